@@ -1,0 +1,165 @@
+/*
+ * tisph.h -- C ABI of libtisph.so, the B200-native (sm_100a) WCSPH step engine.
+ *
+ * The reference (jiajun-c/Ti-SPH) has no FFI layer: its boundary is the Python class
+ * surface (ParticleSystemV4 / WCSPHV2 and the gen-1 2D classes) whose methods are Taichi
+ * kernels.  Each entry point below replaces one group of those Taichi kernels; the Python
+ * classes in core/ and utils/ of this repo keep the reference's names and call these
+ * functions through ctypes (see INTEGRATION.md for the binding).
+ *
+ * Plain C: pointers + sizes only, no torch / C++ types.  Every function returns 0 on
+ * success or a negative tisph_status; the message is available from tisph_last_error().
+ * A context owns all of its device memory and one CUDA stream; it is not thread-safe,
+ * different contexts are independent.  Host arrays are copied, never retained.
+ */
+#ifndef TISPH_H
+#define TISPH_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TISPH_ABI_VERSION 1
+
+typedef struct tisph_ctx tisph_ctx;
+
+typedef enum tisph_status {
+    TISPH_OK = 0,
+    TISPH_ERR_INVALID = -1,      /* bad argument / wrong state */
+    TISPH_ERR_CUDA = -2,         /* CUDA runtime error (message has the detail) */
+    TISPH_ERR_CAPACITY = -3,     /* more particles than config.capacity */
+    TISPH_ERR_DOMAIN = -4,       /* a particle left the grid (reference: undefined behaviour) */
+    TISPH_ERR_NO_DEVICE = -5     /* no CUDA device: there is NO CPU fallback */
+} tisph_status;
+
+/* Scalars are the reference's Python-scope constants, evaluated by the host in float64
+ * exactly as the reference's constructors do and then rounded to f32 (Taichi bakes them
+ * into kernels the same way).  file:line = reference source. */
+typedef struct tisph_config {
+    int32_t struct_size;      /* = sizeof(tisph_config), ABI check */
+    int32_t generation;       /* 2: ParticleSystemV4+WCSPHV2 (3D); 1: ParticleSystem(V2)+WCSPH (2D) */
+    int32_t dim;              /* partice_systemv4.py:17 / partice_system.py:10 */
+    int32_t device;           /* CUDA ordinal */
+    int32_t capacity;         /* particle_max_num, partice_systemv4.py:37-38 / partice_system.py:24 */
+    int32_t grid_num[3];      /* partice_systemv4.py:59 / partice_system.py:30 (z=1 in 2D) */
+    float support;            /* support_length = 4r = grid_size, partice_systemv4.py:34,58 */
+    float padding;            /* partice_systemv4.py:35 */
+    float domain_size[3];     /* partice_systemv4.py:22 */
+    float wall_hi[3];         /* domain_size - padding, sph_basev2.py:164-182 */
+    float m_V0;               /* 0.8 d^dim, partice_systemv4.py:48 / partice_system.py:23 */
+    float dt;                 /* sph_basev2.py:14-15 */
+    float gravity[3];         /* sph_basev2.py:16 ; gen-1: const.py:2 on the last axis */
+    float c_s;                /* wcsphv2.py:16 */
+    float rho0;               /* solver density_0, sph_basev2.py:13 */
+    float ps_density0;        /* ps.density0 (JSON), used at wcsphv2.py:80 */
+    float stiffness;          /* wcsphv2.py:11 */
+    float exponent;           /* wcsphv2.py:10 */
+    float k_w;                /* k/h^dim,  sph_basev2.py:22-30 */
+    float k_dw;               /* 6k/h^dim, sph_basev2.py:42-50 */
+    float visc_fluid_c;       /* 2*viscosity*h*c_s, wcsphv2.py:69 */
+    float visc_bound_c;       /* 0.08*h*c_s, wcsphv2.py:75-76 */
+    float eps_h2;             /* 0.01*h^2, wcsphv2.py:72 / sph_base.py:82 */
+    float g1_visc_c;          /* gen-1: 2*(dim+2)*viscosity, sph_base.py:81 */
+    float g1_mass;            /* gen-1: m_V*density_0, sph_base.py:16 */
+    float g1_press_c;         /* gen-1: -density_0*m_V, sph_base.py:68 */
+    int32_t density_mode;     /* 0 = reference (wcsphv2.py:32-34: sum discarded), 1 = summed */
+    int32_t volume_mode;      /* 0 = reference (sph_basev2.py:191 by-value arg), 1 = akinci */
+    int32_t reserved[8];
+} tisph_config;
+
+/* Per-particle fields, named after the reference's ps.* / solver.* Taichi fields. */
+typedef enum tisph_field {
+    TISPH_F_X = 0,            /* ps.x        f32 [n][dim] */
+    TISPH_F_V = 1,            /* ps.v        f32 [n][dim] */
+    TISPH_F_MASS = 2,         /* ps.mass     f32 [n] */
+    TISPH_F_VOLUME = 3,       /* ps.volume   f32 [n] */
+    TISPH_F_DENSITY = 4,      /* ps.density  f32 [n] */
+    TISPH_F_PRESSURE = 5,     /* ps.pressure f32 [n] */
+    TISPH_F_MATERIAL = 6,     /* ps.material i32 [n] */
+    TISPH_F_COLOR = 7,        /* ps.color    i32 [n][3] (gen-2) / i32 [n] (gen-1) */
+    TISPH_F_GRID_IDS = 8,     /* ps.grid_ids i32 [n] (cell key of each sorted particle) */
+    TISPH_F_GRID_PARTICLES_NUM = 9, /* ps.grid_particles_num i32 [ncell]: INCLUSIVE scan */
+    TISPH_F_D_VELOCITY = 10,  /* solver.d_velocity f32 [n][dim] */
+    /* diagnostics that the reference computes but does not keep */
+    TISPH_F_DENSITY_SUM = 11, /* S_i = sum_j mass_i W(|x_ij|), wcsphv2.py:33   f32 [n] */
+    TISPH_F_DENSITY_RAW = 12, /* density before the clamp of wcsphv2.py:46     f32 [n] */
+    TISPH_F_NEIGHBOR_COUNT = 13, /* #j: j!=i and norm(x_ij) < h, partice_systemv4.py:344  i32 [n] */
+    TISPH_F_ORIG_ID = 14,     /* index the particle had when it was added     i32 [n] */
+    TISPH_F_A_NONPRESSURE = 15, /* d_velocity after wcsphv2.py:93 (needs TISPH_P_DIAGNOSTICS) */
+    TISPH_F_A_PRESSURE = 16,  /* sum added at wcsphv2.py:53 (needs TISPH_P_DIAGNOSTICS) */
+    TISPH_F_CELL_COUNT = 17   /* histogram before the scan, partice_systemv4.py:213  i32 [ncell] */
+} tisph_field;
+
+/* Stages of one step, for stage-by-stage parity tests (tisph_step runs them in order). */
+typedef enum tisph_stage {
+    TISPH_STAGE_UPDATE = 0,   /* ps.update(): key, histogram, scan, stable sort, reorder
+                                 (partice_systemv4.py:251-256) ; gen-1: ps.init() */
+    TISPH_STAGE_DENSITY = 1,  /* compute_volume_of_boundary_particle + compute_densities +
+                                 clamp/EOS (sph_basev2.py:195-201, wcsphv2.py:28-34,45-47) */
+    TISPH_STAGE_FORCE_ADVECT = 2 /* compute_non_pressure_force + compute_pressure_force +
+                                 advert + enforce_boundary (wcsphv2.py:83-100, sph_basev2.py:204) */
+} tisph_stage;
+
+typedef enum tisph_param {
+    TISPH_P_DT = 0,           /* solver.dt[None] */
+    TISPH_P_DENSITY_MODE = 1,
+    TISPH_P_VOLUME_MODE = 2,
+    TISPH_P_DIAGNOSTICS = 3,  /* 1: also store a_nonpressure / a_pressure every step */
+    TISPH_P_KERNEL_VARIANT = 4 /* implementation selector for A/B benchmarking (0 = default) */
+} tisph_param;
+
+const char *tisph_last_error(void);
+int tisph_abi_version(void);
+/* number of visible CUDA devices (0 => every other call fails with TISPH_ERR_NO_DEVICE) */
+int tisph_device_count(void);
+
+/* ParticleSystemV4.__init__ / ParticleSystem.__init__ + WCSPH(V2).__init__: allocate fields. */
+int tisph_create(const tisph_config *cfg, tisph_ctx **out);
+int tisph_destroy(tisph_ctx *ctx);
+
+/* ParticleSystemV4.add_particles (partice_systemv4.py:171-204): append n particles.
+ * pos/vel: [n][dim] f32; density/pressure: [n] f32; material: [n] i32;
+ * color: [n][3] i32 (gen-2) or [n] i32 (gen-1).  mass = m_V0*density, volume = m_V0. */
+int tisph_add_particles(tisph_ctx *ctx, int32_t n, const float *pos, const float *vel,
+                        const float *density, const float *pressure, const int32_t *material,
+                        const int32_t *color);
+/* Forget all particles (particle_num = 0); used to restart from an identical state. */
+int tisph_reset(tisph_ctx *ctx);
+int tisph_particle_num(tisph_ctx *ctx, int32_t *n);
+
+/* SPHBaseV2.step / SPHBase.step (sph_basev2.py:210-214): nsteps whole steps, asynchronous. */
+int tisph_step(tisph_ctx *ctx, int32_t nsteps);
+/* One stage of a step (see tisph_stage); stages must be issued in order. */
+int tisph_stage_run(tisph_ctx *ctx, int32_t stage);
+
+/* ParticleSystemV4.dump / copy_to_numpy (partice_systemv4.py:279-307): synchronous copy of
+ * one field to host memory in the reference's layout; bytes must equal the field size. */
+int tisph_download(tisph_ctx *ctx, int32_t field, void *dst, size_t bytes);
+/* Overwrite x and v of the current particles (current order) from host arrays [n][dim]. */
+int tisph_upload_xv(tisph_ctx *ctx, const float *pos, const float *vel);
+/* Zero-copy hand-off (ggui scene.particles(ps.x), torch, cupy): device pointer of the packed
+ * float4 arrays {x,y,z,mass} (TISPH_F_X) / {vx,vy,vz,volume} (TISPH_F_V) / {ax,ay,az,0}
+ * (TISPH_F_D_VELOCITY); valid until the next step. */
+int tisph_device_ptr(tisph_ctx *ctx, int32_t field, void **ptr, int32_t *stride_bytes);
+
+int tisph_set_param(tisph_ctx *ctx, int32_t param, double value);
+int tisph_get_param(tisph_ctx *ctx, int32_t param, double *value);
+/* Run on a caller-owned cudaStream_t (e.g. torch's current stream); NULL restores the own one. */
+int tisph_set_stream(tisph_ctx *ctx, void *cuda_stream);
+/* Block until the stream is idle and report deferred device-side errors (TISPH_ERR_DOMAIN). */
+int tisph_sync(tisph_ctx *ctx);
+/* Total kernel launches issued by this context so far. */
+int tisph_launch_count(tisph_ctx *ctx, int64_t *launches);
+/* Mean device time (ms, CUDA events on the context's stream) of each stage over the steps
+ * (at most 64) issued since the previous call.  Events are recorded only while `enable`
+ * (as set by the previous call) is non-zero; the call synchronises the stream. */
+int tisph_stage_times(tisph_ctx *ctx, int32_t enable, float *ms_update, float *ms_density,
+                      float *ms_force, int32_t *steps);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TISPH_H */

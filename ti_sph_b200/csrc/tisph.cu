@@ -1,0 +1,506 @@
+// tisph.cu -- host side of libtisph.so: context, stream orchestration and the C ABI declared
+// in include/tisph.h.  There is no CPU fallback: without a CUDA device every call fails.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <new>
+#include <vector>
+
+#include "tisph.h"
+#include "tisph_kernels.cuh"
+
+using namespace tisph;
+
+// ------------------------------------------------------------------------- error plumbing
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CU(call)                                                                          \
+    do {                                                                                  \
+        cudaError_t e_ = (call);                                                          \
+        if (e_ != cudaSuccess)                                                            \
+            return fail(TISPH_ERR_CUDA, "%s failed: %s (%s:%d)", #call,                   \
+                        cudaGetErrorString(e_), __FILE__, __LINE__);                      \
+    } while (0)
+
+#define CHECK_CTX(ctx)                                                                    \
+    do {                                                                                  \
+        if (!(ctx)) return fail(TISPH_ERR_INVALID, "null context");                       \
+        CU(cudaSetDevice((ctx)->cfg.device));                                             \
+    } while (0)
+
+// ------------------------------------------------------------------------------- context
+constexpr int MAX_TIMED_STEPS = 64;
+
+struct tisph_ctx {
+    tisph_config cfg;
+    SimParams sp;
+    int n = 0, cap = 0, ncell = 0;
+    int color_comp = 3;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    float4 *P[2] = {nullptr, nullptr}, *V[2] = {nullptr, nullptr}, *Q[2] = {nullptr, nullptr};
+    int cur = 0;         // which copy holds the authoritative particle records
+    int phase = 0;       // 0: between steps, 1: after UPDATE, 2: after DENSITY
+    bool have_sorted = false;
+    float4 *D = nullptr, *dvel = nullptr, *a_np = nullptr, *a_p = nullptr;
+    float* S = nullptr;
+    int *ncount = nullptr, *keys = nullptr, *arrival = nullptr, *ids = nullptr, *keys_sorted = nullptr;
+    int *cell_count = nullptr, *cell_end = nullptr, *block_sums = nullptr;
+    int* color = nullptr;
+    int* err_dev = nullptr;
+    void* staging = nullptr;
+    size_t staging_bytes = 0;
+    int diagnostics = 0;
+    int variant = 0;
+    int64_t launches = 0;
+    // stage timing
+    int timing = 0, timed = 0;
+    cudaEvent_t ev[MAX_TIMED_STEPS][4];
+    bool ev_made = false;
+};
+
+static float d2_cutoff(float h) {
+    // smallest f32 t with sqrtf(t) >= h, so that (sqrtf(d2) < h) <=> (d2 < t) in IEEE f32
+    float t = h * h;
+    while (sqrtf(t) >= h) t = nextafterf(t, 0.0f);
+    while (sqrtf(t) < h) t = nextafterf(t, INFINITY);
+    return t;
+}
+
+static void fill_params(tisph_ctx* c) {
+    const tisph_config& g = c->cfg;
+    SimParams& s = c->sp;
+    s.n = c->n;
+    s.ncell = c->ncell;
+    s.gx = g.grid_num[0]; s.gy = g.grid_num[1]; s.gz = g.dim == 3 ? g.grid_num[2] : 1;
+    s.dim = g.dim;
+    s.h = g.support;
+    s.inv_h = 1.0f / g.support;
+    s.d2_cut = d2_cutoff(g.support);
+    s.k_w = g.k_w; s.k_dw = g.k_dw;
+    s.dt = g.dt;
+    for (int k = 0; k < 3; ++k) { s.g[k] = g.gravity[k]; s.wall_hi[k] = g.wall_hi[k]; }
+    s.pad = g.padding;
+    s.rho0 = g.rho0; s.ps_density0 = g.ps_density0;
+    s.stiffness = g.stiffness; s.exponent = g.exponent;
+    s.visc_fluid_c = g.visc_fluid_c; s.visc_bound_c = g.visc_bound_c; s.eps_h2 = g.eps_h2;
+    s.g1_visc_c = g.g1_visc_c; s.g1_mass = g.g1_mass; s.g1_press_c = g.g1_press_c;
+    s.m_V0 = g.m_V0;
+    s.density_mode = g.density_mode; s.volume_mode = g.volume_mode;
+    float e = g.exponent;
+    s.int_exponent = (e >= 1.0f && e <= 64.0f && e == floorf(e)) ? (int)e : 0;
+    s.owned_lo = 0;
+    s.owned_hi = 0x7fffffff;
+}
+
+template <typename T>
+static cudaError_t dalloc(T** p, size_t count) {
+    return cudaMalloc((void**)p, count * sizeof(T) + 64);
+}
+
+static inline int nblocks(int n, int t) { return (n + t - 1) / t; }
+
+// ------------------------------------------------------------------------------- stages
+static int run_update(tisph_ctx* c) {
+    if (c->phase != 0) return fail(TISPH_ERR_INVALID, "UPDATE issued out of order (phase %d)", c->phase);
+    if (c->n == 0) return fail(TISPH_ERR_INVALID, "no particles");
+    cudaStream_t st = c->stream;
+    c->sp.n = c->n;
+    int a = c->cur, b = c->cur ^ 1;
+    int nb_cells = nblocks(c->ncell, SCAN_TILE);
+    CU(cudaMemsetAsync(c->cell_count, 0, sizeof(int) * (size_t)c->ncell, st));
+    k_bin<<<nblocks(c->n, 256), 256, 0, st>>>(c->sp, c->P[a], c->keys, c->arrival, c->cell_count, c->err_dev);
+    k_scan_reduce<<<nb_cells, SCAN_THREADS, 0, st>>>(c->cell_count, c->ncell, c->block_sums);
+    k_scan_spine<<<1, 1024, 0, st>>>(c->block_sums, nb_cells);
+    k_scan_apply<<<nb_cells, SCAN_THREADS, 0, st>>>(c->cell_count, c->ncell, c->block_sums, c->cell_end);
+    k_place<<<nblocks(c->n, 256), 256, 0, st>>>(c->n, c->keys, c->arrival, c->cell_end, c->ids);
+    k_reorder<<<nblocks(c->n, 256), 256, 0, st>>>(c->n, c->keys, c->ids, c->cell_end, c->P[a], c->V[a],
+                                                  c->Q[a], c->P[b], c->V[b], c->Q[b], c->keys_sorted);
+    c->launches += 6;
+    CU(cudaGetLastError());
+    c->cur = b;
+    c->phase = 1;
+    c->have_sorted = true;
+    return TISPH_OK;
+}
+
+static int run_density(tisph_ctx* c) {
+    if (c->phase != 1) return fail(TISPH_ERR_INVALID, "DENSITY issued out of order (phase %d)", c->phase);
+    int b = c->cur;
+    k_density<<<c->ncell, NB_THREADS, 0, c->stream>>>(c->sp, c->cell_end, c->P[b], c->V[b], c->Q[b],
+                                                      c->D, c->S, c->ncount);
+    c->launches += 1;
+    CU(cudaGetLastError());
+    c->phase = 2;
+    return TISPH_OK;
+}
+
+static int run_force(tisph_ctx* c) {
+    if (c->phase != 2) return fail(TISPH_ERR_INVALID, "FORCE_ADVECT issued out of order (phase %d)", c->phase);
+    int b = c->cur, a = c->cur ^ 1;
+    k_force<<<c->ncell, NB_THREADS, FORCE_SMEM, c->stream>>>(
+        c->sp, c->cell_end, c->P[b], c->V[b], c->Q[b], c->D, c->P[a], c->V[a], c->Q[a], c->dvel,
+        c->diagnostics ? c->a_np : nullptr, c->diagnostics ? c->a_p : nullptr);
+    c->launches += 1;
+    CU(cudaGetLastError());
+    c->cur = a;
+    c->phase = 0;
+    return TISPH_OK;
+}
+
+// ------------------------------------------------------------------------------- C ABI
+extern "C" {
+
+const char* tisph_last_error(void) { return g_err; }
+int tisph_abi_version(void) { return TISPH_ABI_VERSION; }
+
+int tisph_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int tisph_create(const tisph_config* cfg, tisph_ctx** out) {
+    if (!cfg || !out) return fail(TISPH_ERR_INVALID, "null argument");
+    if (cfg->struct_size != (int32_t)sizeof(tisph_config))
+        return fail(TISPH_ERR_INVALID, "tisph_config size mismatch: got %d, library has %d",
+                    cfg->struct_size, (int)sizeof(tisph_config));
+    if (cfg->generation != 2 || cfg->dim != 3)
+        return fail(TISPH_ERR_INVALID, "only generation 2 / dim 3 is implemented in this build");
+    if (cfg->capacity <= 0 || cfg->support <= 0.f) return fail(TISPH_ERR_INVALID, "bad capacity/support");
+    int64_t ncell = (int64_t)cfg->grid_num[0] * cfg->grid_num[1] * (cfg->dim == 3 ? cfg->grid_num[2] : 1);
+    if (ncell <= 0 || ncell > 0x7fffffff) return fail(TISPH_ERR_INVALID, "grid too large");
+    if (tisph_device_count() <= 0)
+        return fail(TISPH_ERR_NO_DEVICE, "no CUDA device visible; libtisph has no CPU fallback");
+    CU(cudaSetDevice(cfg->device));
+    tisph_ctx* c = new (std::nothrow) tisph_ctx();
+    if (!c) return fail(TISPH_ERR_INVALID, "out of host memory");
+    c->cfg = *cfg;
+    c->cap = cfg->capacity;
+    c->ncell = (int)ncell;
+    c->color_comp = cfg->generation == 2 ? 3 : 1;
+    fill_params(c);
+    size_t cap = (size_t)c->cap;
+    cudaError_t e = cudaSuccess;
+    auto A = [&](cudaError_t r) { if (e == cudaSuccess) e = r; };
+    A(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+    c->stream = c->own_stream;
+    for (int k = 0; k < 2; ++k) { A(dalloc(&c->P[k], cap)); A(dalloc(&c->V[k], cap)); A(dalloc(&c->Q[k], cap)); }
+    A(dalloc(&c->D, cap)); A(dalloc(&c->dvel, cap));
+    A(dalloc(&c->S, cap)); A(dalloc(&c->ncount, cap));
+    A(dalloc(&c->keys, cap)); A(dalloc(&c->arrival, cap)); A(dalloc(&c->ids, cap)); A(dalloc(&c->keys_sorted, cap));
+    A(dalloc(&c->cell_count, (size_t)c->ncell)); A(dalloc(&c->cell_end, (size_t)c->ncell));
+    A(dalloc(&c->block_sums, (size_t)nblocks(c->ncell, SCAN_TILE) + 1024));
+    A(dalloc(&c->color, cap * 3));
+    A(dalloc(&c->err_dev, 4));
+    c->staging_bytes = cap * 16 * 3;
+    A(cudaMalloc(&c->staging, c->staging_bytes));
+    if (e == cudaSuccess) {
+        A(cudaMemsetAsync(c->err_dev, 0, 16, c->stream));
+        A(cudaMemsetAsync(c->dvel, 0, cap * 16, c->stream));
+        A(cudaMemsetAsync(c->S, 0, cap * 4, c->stream));
+        A(cudaMemsetAsync(c->ncount, 0, cap * 4, c->stream));
+        A(cudaMemsetAsync(c->D, 0, cap * 16, c->stream));
+        A(cudaMemsetAsync(c->keys_sorted, 0, cap * 4, c->stream));
+        A(cudaMemsetAsync(c->cell_end, 0, (size_t)c->ncell * 4, c->stream));
+        A(cudaMemsetAsync(c->cell_count, 0, (size_t)c->ncell * 4, c->stream));
+        A(cudaFuncSetAttribute(k_force, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FORCE_SMEM));
+        A(cudaStreamSynchronize(c->stream));
+    }
+    if (e != cudaSuccess) {
+        fail(TISPH_ERR_CUDA, "allocation/initialisation failed: %s", cudaGetErrorString(e));
+        tisph_destroy(c);
+        return TISPH_ERR_CUDA;
+    }
+    *out = c;
+    return TISPH_OK;
+}
+
+int tisph_destroy(tisph_ctx* c) {
+    if (!c) return TISPH_OK;
+    cudaSetDevice(c->cfg.device);
+    if (c->own_stream) cudaStreamSynchronize(c->own_stream);
+    for (int k = 0; k < 2; ++k) { cudaFree(c->P[k]); cudaFree(c->V[k]); cudaFree(c->Q[k]); }
+    cudaFree(c->D); cudaFree(c->dvel); cudaFree(c->a_np); cudaFree(c->a_p); cudaFree(c->S);
+    cudaFree(c->ncount); cudaFree(c->keys); cudaFree(c->arrival); cudaFree(c->ids);
+    cudaFree(c->keys_sorted); cudaFree(c->cell_count); cudaFree(c->cell_end);
+    cudaFree(c->block_sums); cudaFree(c->color); cudaFree(c->err_dev); cudaFree(c->staging);
+    if (c->ev_made)
+        for (int s = 0; s < MAX_TIMED_STEPS; ++s)
+            for (int k = 0; k < 4; ++k) cudaEventDestroy(c->ev[s][k]);
+    if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    delete c;
+    return TISPH_OK;
+}
+
+int tisph_add_particles(tisph_ctx* c, int32_t n, const float* pos, const float* vel,
+                        const float* density, const float* pressure, const int32_t* material,
+                        const int32_t* color) {
+    CHECK_CTX(c);
+    if (n < 0 || !pos || !vel || !density || !pressure || !material)
+        return fail(TISPH_ERR_INVALID, "null/negative argument");
+    if (c->phase != 0) return fail(TISPH_ERR_INVALID, "cannot add particles in the middle of a step");
+    if ((int64_t)c->n + n > c->cap)
+        return fail(TISPH_ERR_CAPACITY, "particle_num %d + %d exceeds particle_max_num %d", c->n, n, c->cap);
+    if (n == 0) return TISPH_OK;
+    int dim = c->cfg.dim;
+    cudaStream_t st = c->stream;
+    // stage in slices so that the staging buffer (48 B/particle) always suffices
+    size_t per = (size_t)(2 * dim + 3) * 4;
+    int max_chunk = (int)(c->staging_bytes / per);
+    for (int done = 0; done < n; done += max_chunk) {
+        int m = n - done < max_chunk ? n - done : max_chunk;
+        char* s = (char*)c->staging;
+        float* d_pos = (float*)s;          s += (size_t)m * dim * 4;
+        float* d_vel = (float*)s;          s += (size_t)m * dim * 4;
+        float* d_rho = (float*)s;          s += (size_t)m * 4;
+        float* d_pr = (float*)s;           s += (size_t)m * 4;
+        int* d_mat = (int*)s;
+        CU(cudaMemcpyAsync(d_pos, pos + (size_t)done * dim, (size_t)m * dim * 4, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(d_vel, vel + (size_t)done * dim, (size_t)m * dim * 4, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(d_rho, density + done, (size_t)m * 4, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(d_pr, pressure + done, (size_t)m * 4, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(d_mat, material + done, (size_t)m * 4, cudaMemcpyHostToDevice, st));
+        k_pack_particles<<<nblocks(m, 256), 256, 0, st>>>(m, dim, c->n + done, c->cfg.m_V0, d_pos, d_vel,
+                                                          d_rho, d_pr, d_mat, c->P[c->cur], c->V[c->cur],
+                                                          c->Q[c->cur]);
+        c->launches += 1;
+        CU(cudaGetLastError());
+        CU(cudaStreamSynchronize(st));   // staging is reused by the next slice
+    }
+    size_t cc = (size_t)c->color_comp;
+    if (color)
+        CU(cudaMemcpyAsync(c->color + (size_t)c->n * cc, color, (size_t)n * cc * 4, cudaMemcpyHostToDevice, st));
+    else
+        CU(cudaMemsetAsync(c->color + (size_t)c->n * cc, 0, (size_t)n * cc * 4, st));
+    CU(cudaStreamSynchronize(st));
+    c->n += n;
+    c->sp.n = c->n;
+    c->have_sorted = false;
+    return TISPH_OK;
+}
+
+int tisph_reset(tisph_ctx* c) {
+    CHECK_CTX(c);
+    CU(cudaStreamSynchronize(c->stream));
+    c->n = 0; c->sp.n = 0; c->phase = 0; c->have_sorted = false;
+    CU(cudaMemsetAsync(c->err_dev, 0, 16, c->stream));
+    return TISPH_OK;
+}
+
+int tisph_particle_num(tisph_ctx* c, int32_t* n) {
+    if (!c || !n) return fail(TISPH_ERR_INVALID, "null argument");
+    *n = c->n;
+    return TISPH_OK;
+}
+
+static int make_events(tisph_ctx* c) {
+    if (c->ev_made) return TISPH_OK;
+    for (int s = 0; s < MAX_TIMED_STEPS; ++s)
+        for (int k = 0; k < 4; ++k) CU(cudaEventCreate(&c->ev[s][k]));
+    c->ev_made = true;
+    return TISPH_OK;
+}
+
+int tisph_step(tisph_ctx* c, int32_t nsteps) {
+    CHECK_CTX(c);
+    if (c->phase != 0) return fail(TISPH_ERR_INVALID, "step issued in the middle of a staged step");
+    for (int s = 0; s < nsteps; ++s) {
+        bool t = c->timing && c->timed < MAX_TIMED_STEPS;
+        int rc;
+        if (t) CU(cudaEventRecord(c->ev[c->timed][0], c->stream));
+        if ((rc = run_update(c))) return rc;
+        if (t) CU(cudaEventRecord(c->ev[c->timed][1], c->stream));
+        if ((rc = run_density(c))) return rc;
+        if (t) CU(cudaEventRecord(c->ev[c->timed][2], c->stream));
+        if ((rc = run_force(c))) return rc;
+        if (t) { CU(cudaEventRecord(c->ev[c->timed][3], c->stream)); c->timed++; }
+    }
+    return TISPH_OK;
+}
+
+int tisph_stage_run(tisph_ctx* c, int32_t stage) {
+    CHECK_CTX(c);
+    switch (stage) {
+        case TISPH_STAGE_UPDATE: return run_update(c);
+        case TISPH_STAGE_DENSITY: return run_density(c);
+        case TISPH_STAGE_FORCE_ADVECT: return run_force(c);
+    }
+    return fail(TISPH_ERR_INVALID, "unknown stage %d", stage);
+}
+
+static int check_device_errors(tisph_ctx* c) {
+    int err[4] = {0, 0, 0, 0};
+    CU(cudaMemcpyAsync(err, c->err_dev, 16, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    if (err[0]) {
+        CU(cudaMemsetAsync(c->err_dev, 0, 16, c->stream));
+        return fail(TISPH_ERR_DOMAIN, "%d particle(s) left the grid (the reference reads out of bounds here)", err[0]);
+    }
+    return TISPH_OK;
+}
+
+int tisph_sync(tisph_ctx* c) {
+    CHECK_CTX(c);
+    CU(cudaStreamSynchronize(c->stream));
+    return check_device_errors(c);
+}
+
+int tisph_download(tisph_ctx* c, int32_t field, void* dst, size_t bytes) {
+    CHECK_CTX(c);
+    if (!dst) return fail(TISPH_ERR_INVALID, "null destination");
+    cudaStream_t st = c->stream;
+    int n = c->n, dim = c->cfg.dim, cur = c->cur;
+    const float4* src = nullptr;
+    int comp0 = 0, ncomp = 1;
+    const void* direct = nullptr;   // already in the reference layout on the device
+    size_t count = (size_t)n;
+    switch (field) {
+        case TISPH_F_X: src = c->P[cur]; comp0 = 0; ncomp = dim; break;
+        case TISPH_F_V: src = c->V[cur]; comp0 = 0; ncomp = dim; break;
+        case TISPH_F_MASS: src = c->P[cur]; comp0 = 3; break;
+        case TISPH_F_VOLUME: src = c->V[cur]; comp0 = 3; break;
+        case TISPH_F_DENSITY: if (c->phase == 2) { src = c->D; comp0 = 2; } else { src = c->Q[cur]; comp0 = 0; } break;
+        case TISPH_F_PRESSURE: if (c->phase == 2) { src = c->D; comp0 = 3; } else { src = c->Q[cur]; comp0 = 1; } break;
+        case TISPH_F_MATERIAL: src = c->Q[cur]; comp0 = 2; break;
+        case TISPH_F_ORIG_ID: src = c->Q[cur]; comp0 = 3; break;
+        case TISPH_F_D_VELOCITY: src = c->dvel; comp0 = 0; ncomp = dim; break;
+        case TISPH_F_DENSITY_RAW: src = c->D; comp0 = 0; break;
+        case TISPH_F_A_NONPRESSURE:
+        case TISPH_F_A_PRESSURE:
+            if (!c->a_np) return fail(TISPH_ERR_INVALID, "enable TISPH_P_DIAGNOSTICS before the step");
+            src = field == TISPH_F_A_NONPRESSURE ? c->a_np : c->a_p; comp0 = 0; ncomp = dim; break;
+        case TISPH_F_DENSITY_SUM: direct = c->S; break;
+        case TISPH_F_NEIGHBOR_COUNT: direct = c->ncount; break;
+        case TISPH_F_GRID_IDS: direct = c->keys_sorted; break;
+        case TISPH_F_GRID_PARTICLES_NUM: direct = c->cell_end; count = (size_t)c->ncell; break;
+        case TISPH_F_CELL_COUNT: direct = c->cell_count; count = (size_t)c->ncell; break;
+        case TISPH_F_COLOR: ncomp = c->color_comp; break;
+        default: return fail(TISPH_ERR_INVALID, "unknown field %d", field);
+    }
+    size_t need = count * (size_t)ncomp * 4;
+    if (bytes != need) return fail(TISPH_ERR_INVALID, "field %d needs %zu bytes, got %zu", field, need, bytes);
+    if (need == 0) return TISPH_OK;
+    if (direct) {
+        CU(cudaMemcpyAsync(dst, direct, need, cudaMemcpyDeviceToHost, st));
+    } else {
+        if (need > c->staging_bytes) return fail(TISPH_ERR_INVALID, "staging buffer too small");
+        if (field == TISPH_F_COLOR)
+            k_gather_color<<<nblocks(n, 256), 256, 0, st>>>(n, ncomp, c->Q[cur], c->color, (int*)c->staging);
+        else
+            k_unpack<<<nblocks(n, 256), 256, 0, st>>>(n, src, comp0, ncomp, (uint32_t*)c->staging);
+        c->launches += 1;
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(dst, c->staging, need, cudaMemcpyDeviceToHost, st));
+    }
+    CU(cudaStreamSynchronize(st));
+    return check_device_errors(c);
+}
+
+int tisph_upload_xv(tisph_ctx* c, const float* pos, const float* vel) {
+    CHECK_CTX(c);
+    if (!pos || !vel) return fail(TISPH_ERR_INVALID, "null argument");
+    if (c->phase != 0) return fail(TISPH_ERR_INVALID, "cannot upload in the middle of a step");
+    int n = c->n, dim = c->cfg.dim;
+    if (n == 0) return TISPH_OK;
+    cudaStream_t st = c->stream;
+    float* d_pos = (float*)c->staging;
+    float* d_vel = d_pos + (size_t)n * dim;
+    CU(cudaMemcpyAsync(d_pos, pos, (size_t)n * dim * 4, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d_vel, vel, (size_t)n * dim * 4, cudaMemcpyHostToDevice, st));
+    k_upload_xv<<<nblocks(n, 256), 256, 0, st>>>(n, dim, d_pos, d_vel, c->P[c->cur], c->V[c->cur]);
+    c->launches += 1;
+    CU(cudaGetLastError());
+    return TISPH_OK;
+}
+
+int tisph_device_ptr(tisph_ctx* c, int32_t field, void** ptr, int32_t* stride_bytes) {
+    if (!c || !ptr) return fail(TISPH_ERR_INVALID, "null argument");
+    switch (field) {
+        case TISPH_F_X: *ptr = c->P[c->cur]; break;
+        case TISPH_F_V: *ptr = c->V[c->cur]; break;
+        case TISPH_F_D_VELOCITY: *ptr = c->dvel; break;
+        default: return fail(TISPH_ERR_INVALID, "field %d has no zero-copy view", field);
+    }
+    if (stride_bytes) *stride_bytes = 16;
+    return TISPH_OK;
+}
+
+int tisph_set_param(tisph_ctx* c, int32_t param, double value) {
+    CHECK_CTX(c);
+    switch (param) {
+        case TISPH_P_DT: c->cfg.dt = (float)value; c->sp.dt = (float)value; return TISPH_OK;
+        case TISPH_P_DENSITY_MODE: c->cfg.density_mode = (int)value; c->sp.density_mode = (int)value; return TISPH_OK;
+        case TISPH_P_VOLUME_MODE: c->cfg.volume_mode = (int)value; c->sp.volume_mode = (int)value; return TISPH_OK;
+        case TISPH_P_DIAGNOSTICS:
+            c->diagnostics = value != 0.0;
+            if (c->diagnostics && !c->a_np) {
+                CU(dalloc(&c->a_np, (size_t)c->cap));
+                CU(dalloc(&c->a_p, (size_t)c->cap));
+                CU(cudaMemsetAsync(c->a_np, 0, (size_t)c->cap * 16, c->stream));
+                CU(cudaMemsetAsync(c->a_p, 0, (size_t)c->cap * 16, c->stream));
+            }
+            return TISPH_OK;
+        case TISPH_P_KERNEL_VARIANT: c->variant = (int)value; return TISPH_OK;
+    }
+    return fail(TISPH_ERR_INVALID, "unknown parameter %d", param);
+}
+
+int tisph_get_param(tisph_ctx* c, int32_t param, double* value) {
+    if (!c || !value) return fail(TISPH_ERR_INVALID, "null argument");
+    switch (param) {
+        case TISPH_P_DT: *value = c->cfg.dt; return TISPH_OK;
+        case TISPH_P_DENSITY_MODE: *value = c->cfg.density_mode; return TISPH_OK;
+        case TISPH_P_VOLUME_MODE: *value = c->cfg.volume_mode; return TISPH_OK;
+        case TISPH_P_DIAGNOSTICS: *value = c->diagnostics; return TISPH_OK;
+        case TISPH_P_KERNEL_VARIANT: *value = c->variant; return TISPH_OK;
+    }
+    return fail(TISPH_ERR_INVALID, "unknown parameter %d", param);
+}
+
+int tisph_set_stream(tisph_ctx* c, void* cuda_stream) {
+    CHECK_CTX(c);
+    CU(cudaStreamSynchronize(c->stream));
+    c->stream = cuda_stream ? (cudaStream_t)cuda_stream : c->own_stream;
+    return TISPH_OK;
+}
+
+int tisph_launch_count(tisph_ctx* c, int64_t* launches) {
+    if (!c || !launches) return fail(TISPH_ERR_INVALID, "null argument");
+    *launches = c->launches;
+    return TISPH_OK;
+}
+
+int tisph_stage_times(tisph_ctx* c, int32_t enable, float* ms_update, float* ms_density,
+                      float* ms_force, int32_t* steps) {
+    CHECK_CTX(c);
+    CU(cudaStreamSynchronize(c->stream));
+    float acc[3] = {0.f, 0.f, 0.f};
+    for (int s = 0; s < c->timed; ++s)
+        for (int k = 0; k < 3; ++k) {
+            float ms = 0.f;
+            CU(cudaEventElapsedTime(&ms, c->ev[s][k], c->ev[s][k + 1]));
+            acc[k] += ms;
+        }
+    int cnt = c->timed;
+    if (ms_update) *ms_update = cnt ? acc[0] / cnt : 0.f;
+    if (ms_density) *ms_density = cnt ? acc[1] / cnt : 0.f;
+    if (ms_force) *ms_force = cnt ? acc[2] / cnt : 0.f;
+    if (steps) *steps = cnt;
+    c->timed = 0;
+    c->timing = enable != 0;
+    if (c->timing) return make_events(c);
+    return TISPH_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,134 @@
+"""Engine: thin object wrapper over the C ABI (include/tisph.h). All compute is CUDA."""
+import ctypes as C
+
+import numpy as np
+
+from . import _capi
+from ._capi import check
+
+_FIELD_SPEC = {   # field -> (dtype, components: 'dim' | int | 'color' | 'cell')
+    _capi.F_X: (np.float32, "dim"), _capi.F_V: (np.float32, "dim"),
+    _capi.F_MASS: (np.float32, 1), _capi.F_VOLUME: (np.float32, 1),
+    _capi.F_DENSITY: (np.float32, 1), _capi.F_PRESSURE: (np.float32, 1),
+    _capi.F_MATERIAL: (np.int32, 1), _capi.F_COLOR: (np.int32, "color"),
+    _capi.F_GRID_IDS: (np.int32, 1), _capi.F_GRID_PARTICLES_NUM: (np.int32, "cell"),
+    _capi.F_D_VELOCITY: (np.float32, "dim"), _capi.F_DENSITY_SUM: (np.float32, 1),
+    _capi.F_DENSITY_RAW: (np.float32, 1), _capi.F_NEIGHBOR_COUNT: (np.int32, 1),
+    _capi.F_ORIG_ID: (np.int32, 1), _capi.F_A_NONPRESSURE: (np.float32, "dim"),
+    _capi.F_A_PRESSURE: (np.float32, "dim"), _capi.F_CELL_COUNT: (np.int32, "cell"),
+}
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class Engine:
+    """One tisph_ctx: device-resident particle state + the step kernels."""
+
+    def __init__(self, config):
+        self._lib = _capi.load()
+        self.config = config
+        self.dim = config.dim
+        self.generation = config.generation
+        self.ncell = int(config.grid_num[0]) * int(config.grid_num[1]) * int(config.grid_num[2])
+        self._ctx = C.c_void_p()
+        check(self._lib.tisph_create(C.byref(config), C.byref(self._ctx)))
+
+    def close(self):
+        if getattr(self, "_ctx", None) and self._ctx.value:
+            self._lib.tisph_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- particles ---------------------------------------------------------------------
+    @property
+    def particle_num(self):
+        n = C.c_int32()
+        check(self._lib.tisph_particle_num(self._ctx, C.byref(n)))
+        return n.value
+
+    def add_particles(self, pos, vel, density, pressure, material, color=None):
+        n = len(pos)
+        pos = np.ascontiguousarray(pos, np.float32).reshape(n, self.dim)
+        vel = np.ascontiguousarray(vel, np.float32).reshape(n, self.dim)
+        density = np.ascontiguousarray(density, np.float32).reshape(n)
+        pressure = np.ascontiguousarray(pressure, np.float32).reshape(n)
+        material = np.ascontiguousarray(material, np.int32).reshape(n)
+        if color is not None:
+            color = np.ascontiguousarray(color, np.int32)
+        check(self._lib.tisph_add_particles(self._ctx, n, _ptr(pos), _ptr(vel), _ptr(density),
+                                            _ptr(pressure), _ptr(material), _ptr(color)))
+
+    def reset(self):
+        check(self._lib.tisph_reset(self._ctx))
+
+    def upload_xv(self, pos, vel):
+        n = self.particle_num
+        pos = np.ascontiguousarray(pos, np.float32).reshape(n, self.dim)
+        vel = np.ascontiguousarray(vel, np.float32).reshape(n, self.dim)
+        check(self._lib.tisph_upload_xv(self._ctx, _ptr(pos), _ptr(vel)))
+
+    # -- stepping ----------------------------------------------------------------------
+    def step(self, nsteps=1):
+        check(self._lib.tisph_step(self._ctx, int(nsteps)))
+
+    def stage(self, stage):
+        check(self._lib.tisph_stage_run(self._ctx, int(stage)))
+
+    def sync(self):
+        check(self._lib.tisph_sync(self._ctx))
+
+    # -- data --------------------------------------------------------------------------
+    def field_shape(self, field):
+        dtype, comp = _FIELD_SPEC[field]
+        n = self.particle_num
+        if comp == "cell":
+            return dtype, (self.ncell,)
+        if comp == "dim":
+            return dtype, (n, self.dim)
+        if comp == "color":
+            return dtype, ((n, 3) if self.generation == 2 else (n,))
+        return dtype, (n,)
+
+    def download(self, field, out=None):
+        dtype, shape = self.field_shape(field)
+        if out is None:
+            out = np.empty(shape, dtype)
+        assert out.dtype == dtype and out.flags.c_contiguous and out.size == int(np.prod(shape))
+        check(self._lib.tisph_download(self._ctx, int(field), _ptr(out), out.nbytes))
+        return out
+
+    def device_ptr(self, field):
+        p, stride = C.c_void_p(), C.c_int32()
+        check(self._lib.tisph_device_ptr(self._ctx, int(field), C.byref(p), C.byref(stride)))
+        return p.value, stride.value
+
+    # -- parameters ----------------------------------------------------------------------
+    def set_param(self, param, value):
+        check(self._lib.tisph_set_param(self._ctx, int(param), float(value)))
+
+    def get_param(self, param):
+        v = C.c_double()
+        check(self._lib.tisph_get_param(self._ctx, int(param), C.byref(v)))
+        return v.value
+
+    def set_stream(self, cuda_stream):
+        check(self._lib.tisph_set_stream(self._ctx, C.c_void_p(cuda_stream or 0)))
+
+    @property
+    def launch_count(self):
+        v = C.c_int64()
+        check(self._lib.tisph_launch_count(self._ctx, C.byref(v)))
+        return v.value
+
+    def stage_times(self, enable=True):
+        a, b, c, s = C.c_float(), C.c_float(), C.c_float(), C.c_int32()
+        check(self._lib.tisph_stage_times(self._ctx, int(bool(enable)), C.byref(a), C.byref(b),
+                                          C.byref(c), C.byref(s)))
+        return {"update_ms": a.value, "density_ms": b.value, "force_ms": c.value, "steps": s.value}
