@@ -1,0 +1,324 @@
+#!/usr/bin/env python
+"""bench.py -- particle-updates/s of one full WCSPH step (BASELINE.json metric).
+
+  python bench.py --gpus N --steps K --warmup W            # the CUDA engine (this repo)
+  python bench.py --impl reference ...                      # CPU restatement of the reference
+
+A "step" is SPHBaseV2.step(): bin/scan/sort/reorder, density+EOS, forces+advect+walls over the
+whole particle set.  Workload at N=1: C5 of BASELINE.md, the 16 M-particle 3D dam break the
+metric is quoted on (`--workload C3` gives the 1 M run).  `value` has the state resident in HBM;
+`e2e` goes through the drop-in classes (ParticleSystemV4 / WCSPHV2) with host buffers: pinned
+host x,v -> device, step(), dump() -> host, every step.  One JSON line on stdout (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "particle_updates_per_sec"
+UNIT = "particle-updates/s"
+# algorithmic HBM bytes per particle-step
+BYTES_STEP = {"reference": 170.0, "summed": 186.0}
+BYTES_FORCE = 68.0      # fused forces+advect+walls: R {x,v,mass,volume,material,rho,p} 44 + W {x,v} 24
+BYTES_DENSITY = {"reference": 8.0, "summed": 24.0}
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.path = tempfile.mktemp(suffix=".csv")
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(gpu_index), f"--query-gpu={self.Q}",
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        try:
+            for line in open(self.path):
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1])); mx.append(float(f[2]))
+                except ValueError:
+                    continue
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                                      "sw_power_cap"), f[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)),
+                   "reasons": sorted(reasons), "samples": len(sm)}
+        return out
+
+
+def workload_scene(name):
+    from ti_sph_b200 import scene as sc
+    return sc.bench_scene(name)
+
+
+def sample_scene(name, target_particles):
+    """A bounded sample of workload `name` for the CPU legs: same radius/grid/velocity, the
+    fluid block cut down along x then y to ~target_particles."""
+    s = workload_scene(name)
+    blk = s["fluidBlocks"][0]
+    r = s["configuration"]["particleRadius"]
+    dims = [int(round((blk["end"][i] - blk["start"][i]) / r)) for i in range(3)]
+    n = dims[0] * dims[1] * dims[2]
+    for ax in (0, 1, 2):
+        while n > target_particles * 1.5 and dims[ax] > 40:
+            dims[ax] //= 2
+            n = dims[0] * dims[1] * dims[2]
+    blk["end"] = [blk["start"][i] + dims[i] * r for i in range(3)]
+    return s
+
+
+# ----------------------------------------------------------------------------- CPU legs
+def cpu_leg(workload, mode, steps, warmup, target_particles):
+    """Times the CPU oracle (restatement of the reference's kernels, oracle/) on host cores."""
+    from oracle.oracle import Gen2Oracle, lib
+    scene = sample_scene(workload, target_particles)
+    ora = Gen2Oracle(scene, density_mode=mode)
+    cores = lib().ora_num_threads()
+    for _ in range(warmup):
+        ora.step_fast(1)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        ora.step_fast(1)
+    dt = (time.perf_counter() - t0) / max(steps, 1)
+    blk = scene["fluidBlocks"][0]
+    sample = (f"{ora.n} particles: block {blk['start']}-{[round(e, 4) for e in blk['end']]} of {workload} "
+              f"(r={scene['configuration']['particleRadius']}), {steps} step(s) after {warmup} warm-up")
+    return {"value": ora.n / dt, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+            "ms_per_step": dt * 1e3, "n": ora.n}
+
+
+def run_reference_impl(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    leg = cpu_leg(args.workload, args.mode, args.steps, args.warmup, args.ref_particles)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": leg["value"], "unit": UNIT,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": leg["ms_per_step"], "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.workload} (bounded sample)", "density_mode": args.mode,
+                   "particles": leg["n"]},
+        "cpu_baseline": {k: leg[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": leg["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "Taichi is not installable here, so the reference's own kernels cannot run; this is "
+                "the CPU restatement of them (oracle/sph_oracle.c, OpenMP over all host threads)",
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------- GPU arm
+def run_gpu(args):
+    import torch
+    from ti_sph_b200 import _capi as K
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the engine has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    scene = workload_scene(args.workload)
+    hbm_peak, peak_kind = measured_peaks()
+
+    if world == 1:
+        from core.partice_system.partice_systemv4 import ParticleSystemV4
+        from core.sph.wcsphv2 import WCSPHV2
+        t0 = time.time()
+        ps = ParticleSystemV4(scene, device=local_rank, density_mode=args.mode)
+        solver = WCSPHV2(ps)
+        eng = ps.engine
+        stream = torch.cuda.Stream()
+        torch.cuda.set_stream(stream)      # torch events and the engine share this stream
+        eng.set_stream(stream.cuda_stream)
+        n_total = eng.particle_num
+        log(f"[bench] {args.workload}: {n_total} particles set up in {time.time() - t0:.1f}s")
+        step = lambda k=1: eng.step(k)
+        sim = None
+    else:
+        from ti_sph_b200.sharded import ShardedSim
+        sim = ShardedSim(scene, density_mode=args.mode, device=local_rank)
+        eng = sim.engine
+        n_total = sim.global_particle_num
+        step = lambda k=1: sim.step(k)
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing ---------------------------------------------------------
+    step(args.warmup)
+    barrier()
+    eng.stage_times(True)
+    l0 = eng.launch_count
+    clocks = ClockSampler(local_rank)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    step(args.steps)
+    ev1.record()
+    barrier()
+    clk = clocks.stop()
+    ms = ev0.elapsed_time(ev1) / args.steps
+    launches = eng.launch_count - l0
+    stage = eng.stage_times(False)
+    if world > 1:
+        import torch.distributed as dist
+        t = torch.tensor([ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        lt = torch.tensor([launches], device="cuda", dtype=torch.int64)
+        dist.all_reduce(lt, op=dist.ReduceOp.SUM)
+        launches = int(lt.item())
+    value = n_total / (ms * 1e-3)
+
+    # ---- end-to-end through the drop-in classes, host buffers ------------------------------
+    e2e = None
+    if world == 1:
+        n = n_total
+        e2e_steps = max(1, min(args.steps, args.e2e_steps))
+        host = ps.dump()
+        pin = {k: torch.empty(v.shape, dtype=torch.float32 if v.dtype == np.float32 else torch.int32).pin_memory()
+               for k, v in host.items()}
+        hx, hv = pin["position"].numpy(), pin["velocity"].numpy()
+        hx[:] = host["position"]; hv[:] = host["velocity"]
+        outs = {k: v.numpy() for k, v in pin.items()}
+        h2d = hx.nbytes + hv.nbytes
+        d2h = sum(v.nbytes for v in outs.values())
+
+        def e2e_step():
+            eng.upload_xv(hx, hv)          # host -> device: this step's input state
+            solver.step()
+            ps.dump(out=outs)              # device -> host: the step's result (position/velocity/material/color)
+
+        e2e_step()
+        barrier()
+        ev0.record()
+        for _ in range(e2e_steps):
+            e2e_step()
+        ev1.record()
+        barrier()
+        ems = ev0.elapsed_time(ev1) / e2e_steps
+        e2e = {"value": n / (ems * 1e-3), "unit": UNIT, "ms_per_step": ems, "steps": e2e_steps,
+               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+               "api": "ParticleSystemV4.engine.upload_xv + WCSPHV2.step + ParticleSystemV4.dump"}
+
+    if rank != 0:
+        return
+    # ---- roofline of the dominant kernel (k_force), measured live with CUDA events --------
+    n_local = eng.particle_num
+    force_s = stage["force_ms"] * 1e-3
+    achieved = BYTES_FORCE * n_local / force_s / 1e9 if force_s > 0 else 0.0
+    roofline = {
+        "bound": "hbm", "kernel": "k_force (forces+advect+walls)", "achieved": achieved,
+        "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "peak_kind": peak_kind,
+        "traffic": None, "bytes_per_particle": BYTES_FORCE, "launch_ms": stage["force_ms"],
+        "step_hbm_frac": BYTES_STEP[args.mode] * n_total / (ms * 1e-3) / 1e9 / hbm_peak / world,
+        "stage_ms": {k: stage[k] for k in ("update_ms", "density_ms", "force_ms")},
+        "note": "the step is FP32-issue-bound at the reference's h = 4 x spacing (1728 candidates, "
+                "~232 neighbours per particle and walk); see DESIGN.md section 5",
+    }
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        leg = cpu_leg(args.workload, args.mode, 1, 1, args.cpu_particles)
+        cpu = {k: leg[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: 3D WCSPH dam break, {n_total} particles "
+                               f"(BASELINE.md {args.workload})",
+                   "particles": n_total, "density_mode": args.mode,
+                   "l2": "state (48 B/particle x 2 copies) larger than L2" if n_total * 96 > 126e6
+                         else "state fits L2 (small workload)",
+                   "parallelism": "single GPU" if world == 1 else f"x-slabs x{world}, halo exchange over NCCL"},
+        "clocks": clk, "gpu_launches": int(launches), "roofline": roofline,
+    }
+    if e2e is not None:
+        line["e2e"] = e2e
+    if cpu is not None:
+        line["cpu_baseline"] = cpu
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="tisph", choices=["tisph", "reference"])
+    ap.add_argument("--workload", default="C5", choices=["C2", "C3", "C4", "C5"])
+    ap.add_argument("--mode", default="reference", choices=["reference", "summed"],
+                    help="density mode: reference = bit-faithful to wcsphv2.py:32-34, summed = intent")
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--cpu-particles", type=int, default=500000, help="size of the cpu_baseline sample")
+    ap.add_argument("--ref-particles", type=int, default=250000, help="sample size of --impl reference")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        log("[bench] warm-up raised to 3 (timing rules)")
+        args.warmup = 3
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        return run_reference_impl(args)
+    if world == 1 and args.gpus > 1:
+        # launched without torchrun: re-launch ourselves one rank per GPU
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", "29531", os.path.abspath(__file__)] + sys.argv[1:]
+        raise SystemExit(subprocess.call(cmd))
+    run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

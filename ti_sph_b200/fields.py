@@ -1,0 +1,90 @@
+"""Field views: what the reference exposes as Taichi fields (`ps.x`, `ps.v`, `solver.dt`, ...).
+
+A FieldView never copies on its own: `.to_numpy()` is a device->host copy of the field in the
+reference's layout, `__cuda_array_interface__` / `.to_torch()` are zero-copy views of the packed
+float4 records on the device (what `scene.particles(ps.x)` needs, main_3d.py:41), and
+`.to_taichi()` mirrors into a Taichi field when Taichi is importable.
+"""
+import numpy as np
+
+from . import _capi as K
+
+_ZERO_COPY = (K.F_X, K.F_V, K.F_D_VELOCITY)
+
+
+class FieldView:
+    def __init__(self, owner, field, name):
+        self._owner = owner          # object with an `.engine`
+        self._field = field
+        self.name = name
+
+    @property
+    def _eng(self):
+        return self._owner.engine
+
+    @property
+    def dtype(self):
+        return np.dtype(self._eng.field_shape(self._field)[0])
+
+    @property
+    def shape(self):
+        # Taichi fields are sized particle_max_num / ncell; vector width is not part of shape
+        shp = self._eng.field_shape(self._field)[1]
+        return shp[:1]
+
+    def to_numpy(self):
+        return self._eng.download(self._field)
+
+    def __array__(self, dtype=None, copy=None):
+        a = self.to_numpy()
+        return a if dtype is None else a.astype(dtype)
+
+    def __len__(self):
+        return self.shape[0]
+
+    def __getitem__(self, idx):
+        return self.to_numpy()[idx]
+
+    @property
+    def __cuda_array_interface__(self):
+        if self._field not in _ZERO_COPY:
+            raise AttributeError(f"{self.name} has no zero-copy device view; use to_numpy()")
+        ptr, stride = self._eng.device_ptr(self._field)
+        n = self._eng.particle_num
+        return {"shape": (n, self._eng.dim), "typestr": "<f4", "data": (ptr, False),
+                "strides": (stride, 4), "version": 3}
+
+    def to_torch(self, device=None):
+        import torch
+        return torch.as_tensor(self, device=device or "cuda")
+
+    def to_taichi(self):
+        import taichi as ti     # optional: only for the ggui hand-off
+        a = self.to_numpy()
+        if a.ndim == 2:
+            f = ti.Vector.field(a.shape[1], dtype=ti.f32 if a.dtype == np.float32 else ti.i32,
+                                shape=a.shape[0])
+        else:
+            f = ti.field(dtype=ti.f32 if a.dtype == np.float32 else ti.i32, shape=a.shape[0])
+        f.from_numpy(a)
+        return f
+
+
+class ScalarView:
+    """0-d field (`ps.particle_num[None]`, `solver.dt[None]`)."""
+
+    def __init__(self, getter, setter=None):
+        self._get, self._set = getter, setter
+
+    def __getitem__(self, idx):
+        assert idx is None
+        return self._get()
+
+    def __setitem__(self, idx, value):
+        assert idx is None
+        if self._set is None:
+            raise TypeError("read-only field")
+        self._set(value)
+
+    def to_numpy(self):
+        return np.asarray(self._get())
