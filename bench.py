@@ -198,7 +198,30 @@ def run_gpu(args):
         torch.cuda.synchronize()
 
     # ---- device-resident timing ---------------------------------------------------------
-    step(args.warmup)
+    # The reference-mode dam break has no working pressure (wcsphv2.py:32-34 discards the density
+    # sum) and clumps within a few dozen steps, after which the cost of a step explodes. So the
+    # bench replays a saved state: PRE steps from the t=0 lattice, save, then chains of CHAIN steps
+    # each restarted from the saved state (one device-to-device restore per chain, inside the timed
+    # region). Every timed step is a full step on simulated steps PRE..PRE+CHAIN of the dam break.
+    PRE, CHAIN = args.pre_steps, args.chain
+
+    def run_steps(k):
+        done = 0
+        while done < k:
+            m = min(CHAIN, k - done)
+            if sim is None:
+                eng.restore_state()
+            else:
+                sim.restore_state()
+            step(m)
+            done += m
+
+    step(PRE)
+    if sim is None:
+        eng.save_state()
+    else:
+        sim.save_state()
+    run_steps(args.warmup)
     barrier()
     eng.stage_times(True)
     l0 = eng.launch_count
@@ -206,7 +229,7 @@ def run_gpu(args):
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ev0.record()
-    step(args.steps)
+    run_steps(args.steps)
     ev1.record()
     barrier()
     clk = clocks.stop()
@@ -228,19 +251,28 @@ def run_gpu(args):
     if world == 1:
         n = n_total
         e2e_steps = max(1, min(args.steps, args.e2e_steps))
+        eng.restore_state()
         host = ps.dump()
-        pin = {k: torch.empty(v.shape, dtype=torch.float32 if v.dtype == np.float32 else torch.int32).pin_memory()
-               for k, v in host.items()}
-        hx, hv = pin["position"].numpy(), pin["velocity"].numpy()
+
+        def pinned(a):
+            return torch.empty(a.shape, dtype=torch.float32 if a.dtype == np.float32 else torch.int32).pin_memory().numpy()
+
+        hx, hv = pinned(host["position"]), pinned(host["velocity"])      # the step's input, on the host
         hx[:] = host["position"]; hv[:] = host["velocity"]
-        outs = {k: v.numpy() for k, v in pin.items()}
+        outs = {k: pinned(v) for k, v in host.items()}                    # the step's result, on the host
         h2d = hx.nbytes + hv.nbytes
         d2h = sum(v.nbytes for v in outs.values())
 
+        dbg = os.environ.get("BENCH_DEBUG")
+
         def e2e_step():
+            t0 = time.time()
             eng.upload_xv(hx, hv)          # host -> device: this step's input state
+            if dbg: eng.sync(); log(f"[e2e] upload {time.time() - t0:.3f}s")
             solver.step()
+            if dbg: eng.sync(); log(f"[e2e] step {time.time() - t0:.3f}s")
             ps.dump(out=outs)              # device -> host: the step's result (position/velocity/material/color)
+            if dbg: log(f"[e2e] dump {time.time() - t0:.3f}s")
 
         e2e_step()
         barrier()
@@ -280,6 +312,8 @@ def run_gpu(args):
         "config": {"workload": f"{args.workload}: 3D WCSPH dam break, {n_total} particles "
                                f"(BASELINE.md {args.workload})",
                    "particles": n_total, "density_mode": args.mode,
+                   "state": f"dam-break block after {PRE} steps from the t=0 lattice; replayed in chains of "
+                            f"{CHAIN} steps (device-side restore inside the timed region)",
                    "l2": "state (48 B/particle x 2 copies) larger than L2" if n_total * 96 > 126e6
                          else "state fits L2 (small workload)",
                    "parallelism": "single GPU" if world == 1 else f"x-slabs x{world}, halo exchange over NCCL"},
@@ -302,6 +336,8 @@ def main():
     ap.add_argument("--mode", default="reference", choices=["reference", "summed"],
                     help="density mode: reference = bit-faithful to wcsphv2.py:32-34, summed = intent")
     ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--pre-steps", type=int, default=5, help="steps from the lattice before the state is saved")
+    ap.add_argument("--chain", type=int, default=5, help="steps per replay chain (main_3d.py renders every 5)")
     ap.add_argument("--cpu-particles", type=int, default=500000, help="size of the cpu_baseline sample")
     ap.add_argument("--ref-particles", type=int, default=250000, help="sample size of --impl reference")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -129,6 +129,12 @@ int tisph_add_particles(tisph_ctx *ctx, int32_t n, const float *pos, const float
 /* Forget all particles (particle_num = 0); used to restart from an identical state. */
 int tisph_reset(tisph_ctx *ctx);
 int tisph_particle_num(tisph_ctx *ctx, int32_t *n);
+/* Device-resident checkpoint of the particle records (x, v, mass, volume, density, pressure,
+ * material, ids) in their current order; restore makes it the current state again.  The
+ * reference has no checkpointing (its JSON `outputInterval` is unused); bench.py uses this to
+ * replay the same synthetic state. */
+int tisph_state_save(tisph_ctx *ctx);
+int tisph_state_restore(tisph_ctx *ctx);
 
 /* SPHBaseV2.step / SPHBase.step (sph_basev2.py:210-214): nsteps whole steps, asynchronous. */
 int tisph_step(tisph_ctx *ctx, int32_t nsteps);

@@ -54,6 +54,8 @@ SYMBOLS = {
     "tisph_add_particles": (C.c_int, [_vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "tisph_reset": (C.c_int, [_vp]),
     "tisph_particle_num": (C.c_int, [_vp, _ip]),
+    "tisph_state_save": (C.c_int, [_vp]),
+    "tisph_state_restore": (C.c_int, [_vp]),
     "tisph_step": (C.c_int, [_vp, _i32]),
     "tisph_stage_run": (C.c_int, [_vp, _i32]),
     "tisph_download": (C.c_int, [_vp, _i32, _vp, C.c_size_t]),

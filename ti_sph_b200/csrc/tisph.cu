@@ -60,6 +60,8 @@ struct tisph_ctx {
     int* err_dev = nullptr;
     void* staging = nullptr;
     size_t staging_bytes = 0;
+    float4 *snapP = nullptr, *snapV = nullptr, *snapQ = nullptr;   // tisph_state_save
+    int snap_n = -1;
     int diagnostics = 0;
     int variant = 0;
     int64_t launches = 0;
@@ -137,8 +139,12 @@ static int run_update(tisph_ctx* c) {
 static int run_density(tisph_ctx* c) {
     if (c->phase != 1) return fail(TISPH_ERR_INVALID, "DENSITY issued out of order (phase %d)", c->phase);
     int b = c->cur;
-    k_density<<<c->ncell, NB_THREADS, 0, c->stream>>>(c->sp, c->cell_end, c->P[b], c->V[b], c->Q[b],
-                                                      c->D, c->S, c->ncount);
+    if (c->variant == 1)
+        k_density<<<c->ncell, NB_THREADS, 0, c->stream>>>(c->sp, c->cell_end, c->P[b], c->V[b], c->Q[b],
+                                                          c->D, c->S, c->ncount);
+    else
+        k_density2<<<c->ncell, NB_THREADS, D2_SMEM, c->stream>>>(c->sp, c->cell_end, c->P[b], c->V[b],
+                                                                 c->Q[b], c->D, c->S, c->ncount);
     c->launches += 1;
     CU(cudaGetLastError());
     c->phase = 2;
@@ -148,9 +154,14 @@ static int run_density(tisph_ctx* c) {
 static int run_force(tisph_ctx* c) {
     if (c->phase != 2) return fail(TISPH_ERR_INVALID, "FORCE_ADVECT issued out of order (phase %d)", c->phase);
     int b = c->cur, a = c->cur ^ 1;
-    k_force<<<c->ncell, NB_THREADS, FORCE_SMEM, c->stream>>>(
-        c->sp, c->cell_end, c->P[b], c->V[b], c->Q[b], c->D, c->P[a], c->V[a], c->Q[a], c->dvel,
-        c->diagnostics ? c->a_np : nullptr, c->diagnostics ? c->a_p : nullptr);
+    float4* dnp = c->diagnostics ? c->a_np : nullptr;
+    float4* dp = c->diagnostics ? c->a_p : nullptr;
+    if (c->variant == 1)
+        k_force<<<c->ncell, NB_THREADS, FORCE_SMEM, c->stream>>>(
+            c->sp, c->cell_end, c->P[b], c->V[b], c->Q[b], c->D, c->P[a], c->V[a], c->Q[a], c->dvel, dnp, dp);
+    else
+        k_force2<<<c->ncell, NB_THREADS, F2_SMEM, c->stream>>>(
+            c->sp, c->cell_end, c->P[b], c->V[b], c->Q[b], c->D, c->P[a], c->V[a], c->Q[a], c->dvel, dnp, dp);
     c->launches += 1;
     CU(cudaGetLastError());
     c->cur = a;
@@ -215,6 +226,8 @@ int tisph_create(const tisph_config* cfg, tisph_ctx** out) {
         A(cudaMemsetAsync(c->cell_end, 0, (size_t)c->ncell * 4, c->stream));
         A(cudaMemsetAsync(c->cell_count, 0, (size_t)c->ncell * 4, c->stream));
         A(cudaFuncSetAttribute(k_force, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FORCE_SMEM));
+        A(cudaFuncSetAttribute(k_force2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F2_SMEM));
+        A(cudaFuncSetAttribute(k_density2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)D2_SMEM));
         A(cudaStreamSynchronize(c->stream));
     }
     if (e != cudaSuccess) {
@@ -234,6 +247,7 @@ int tisph_destroy(tisph_ctx* c) {
     cudaFree(c->D); cudaFree(c->dvel); cudaFree(c->a_np); cudaFree(c->a_p); cudaFree(c->S);
     cudaFree(c->ncount); cudaFree(c->keys); cudaFree(c->arrival); cudaFree(c->ids);
     cudaFree(c->keys_sorted); cudaFree(c->cell_count); cudaFree(c->cell_end);
+    cudaFree(c->snapP); cudaFree(c->snapV); cudaFree(c->snapQ);
     cudaFree(c->block_sums); cudaFree(c->color); cudaFree(c->err_dev); cudaFree(c->staging);
     if (c->ev_made)
         for (int s = 0; s < MAX_TIMED_STEPS; ++s)
@@ -301,6 +315,33 @@ int tisph_reset(tisph_ctx* c) {
 int tisph_particle_num(tisph_ctx* c, int32_t* n) {
     if (!c || !n) return fail(TISPH_ERR_INVALID, "null argument");
     *n = c->n;
+    return TISPH_OK;
+}
+
+int tisph_state_save(tisph_ctx* c) {
+    CHECK_CTX(c);
+    if (c->phase != 0) return fail(TISPH_ERR_INVALID, "cannot save in the middle of a step");
+    size_t cap = (size_t)c->cap;
+    if (!c->snapP) { CU(dalloc(&c->snapP, cap)); CU(dalloc(&c->snapV, cap)); CU(dalloc(&c->snapQ, cap)); }
+    size_t bytes = (size_t)c->n * sizeof(float4);
+    CU(cudaMemcpyAsync(c->snapP, c->P[c->cur], bytes, cudaMemcpyDeviceToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->snapV, c->V[c->cur], bytes, cudaMemcpyDeviceToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->snapQ, c->Q[c->cur], bytes, cudaMemcpyDeviceToDevice, c->stream));
+    c->snap_n = c->n;
+    return TISPH_OK;
+}
+
+int tisph_state_restore(tisph_ctx* c) {
+    CHECK_CTX(c);
+    if (c->snap_n < 0) return fail(TISPH_ERR_INVALID, "no saved state");
+    if (c->phase != 0) return fail(TISPH_ERR_INVALID, "cannot restore in the middle of a step");
+    size_t bytes = (size_t)c->snap_n * sizeof(float4);
+    CU(cudaMemcpyAsync(c->P[c->cur], c->snapP, bytes, cudaMemcpyDeviceToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->V[c->cur], c->snapV, bytes, cudaMemcpyDeviceToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->Q[c->cur], c->snapQ, bytes, cudaMemcpyDeviceToDevice, c->stream));
+    c->n = c->snap_n;
+    c->sp.n = c->n;
+    c->have_sorted = false;
     return TISPH_OK;
 }
 

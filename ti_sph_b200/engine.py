@@ -68,6 +68,12 @@ class Engine:
     def reset(self):
         check(self._lib.tisph_reset(self._ctx))
 
+    def save_state(self):
+        check(self._lib.tisph_state_save(self._ctx))
+
+    def restore_state(self):
+        check(self._lib.tisph_state_restore(self._ctx))
+
     def upload_xv(self, pos, vel):
         n = self.particle_num
         pos = np.ascontiguousarray(pos, np.float32).reshape(n, self.dim)
