@@ -12,7 +12,7 @@ from util import RTOL, jitter, make_pair, rel_err, small_scene, vec_rel_err
 pytestmark = pytest.mark.gpu
 
 
-def run_stages(ora, eng, density_mode):
+def run_stages(ora, eng, density_mode, p_rtol=RTOL, np_floor=None):
     t = ora.step(trace=True)
     eng.set_param(K.P_DIAGNOSTICS, 1)
     # ---- ps.update(): integer work, bit-exact
@@ -30,10 +30,10 @@ def run_stages(ora, eng, density_mode):
     assert rel_err(eng.download(K.F_DENSITY_RAW), t["density_pre"]) < RTOL
     rho = eng.download(K.F_DENSITY)
     assert rel_err(rho, t["density"]) < RTOL
-    # p = 50 (x^7 - 1) cancels near x = 1: |dp| <= 1e-5 |p| + 50*8*eps*x^7
+    # p = 50 (x^7 - 1) cancels near x = 1: |dp| <= p_rtol |p| + 50*8*eps*x^7
     p, p_ref = eng.download(K.F_PRESSURE).astype(np.float64), t["pressure"].astype(np.float64)
     x7 = (t["density"].astype(np.float64) / 1000.0) ** 7
-    assert np.all(np.abs(p - p_ref) <= RTOL * np.abs(p_ref) + 50 * 8 * np.finfo(np.float32).eps * x7)
+    assert np.all(np.abs(p - p_ref) <= p_rtol * np.abs(p_ref) + 50 * 8 * np.finfo(np.float32).eps * x7)
     assert np.array_equal(eng.download(K.F_VOLUME), t["volume"]) or \
         rel_err(eng.download(K.F_VOLUME), t["volume"]) < RTOL
     # ---- forces + advect + walls
@@ -42,7 +42,8 @@ def run_stages(ora, eng, density_mode):
     a_np, a_p = eng.download(K.F_A_NONPRESSURE), eng.download(K.F_A_PRESSURE)
     # accelerations are sums with cancellation: compare norm-relative with a floor that is the
     # magnitude of the summands (|g| in reference mode, the pressure terms in summed mode)
-    assert vec_rel_err(a_np, t["a_nonpressure"], floor=g) < RTOL
+    # (stress cases pass np_floor = the magnitude of the partial sums that cancel)
+    assert vec_rel_err(a_np, t["a_nonpressure"], floor=np_floor or g) < RTOL
     pfloor = max(g, float(np.percentile(np.linalg.norm(t["a_pressure"], axis=1), 99)))
     assert vec_rel_err(a_p, t["a_pressure"], floor=pfloor) < 5 * RTOL
     assert vec_rel_err(eng.download(K.F_D_VELOCITY), t["d_velocity"], floor=pfloor) < 5 * RTOL
@@ -57,9 +58,12 @@ def run_stages(ora, eng, density_mode):
     return t
 
 
+@pytest.mark.parametrize("variant", [0, 1], ids=["lists", "fallback"])
 @pytest.mark.parametrize("density_mode", ["reference", "summed"])
 @pytest.mark.parametrize("state", ["lattice", "jitter"])
-def test_single_step_parity(density_mode, state):
+def test_single_step_parity(density_mode, state, variant):
+    """variant 0: packed-f32x2 filter + neighbour lists handed from the density walk to the force
+    walk; variant 1: every work item through the self-contained fallback kernels."""
     scene = small_scene()
     x = None
     if state == "jitter":
@@ -67,7 +71,62 @@ def test_single_step_parity(density_mode, state):
         x = jitter(ora0.x, 0.01)
         eng0.close()
     ora, eng = make_pair(scene, density_mode=density_mode, x=x)
+    eng.set_param(K.P_KERNEL_VARIANT, variant)
     run_stages(ora, eng, density_mode)
+    eng.close()
+
+
+def _custom_pair(x, density_mode="summed"):
+    """oracle + engine holding arbitrary fluid positions (demo_3d constants, v = 0)."""
+    from oracle.oracle import Gen2Oracle
+    from ti_sph_b200 import scene as sc
+    from ti_sph_b200.engine import Engine
+    scene = small_scene()
+    ora = Gen2Oracle(scene, density_mode=density_mode)
+    n = len(x)
+    v = np.zeros((n, 3), np.float32)
+    v[:, 1] = -1.0
+    ora.set_state(x, v, np.full(n, 1000.0, np.float32), np.ones(n, np.int32))
+    eng = Engine(sc.gen2_config(scene["configuration"], n, density_mode={"reference": 0, "summed": 1}[density_mode]))
+    eng.add_particles(ora.x, ora.v, ora.density, ora.pressure, ora.material, ora.color)
+    return ora, eng
+
+
+def test_crowded_cells_take_the_fallback_path():
+    """512 particles per cell (spacing r/2): the 27-cell tile (13,824 candidates) exceeds the
+    shared-memory tile, cells split into several work items, multi-tile fallback kernels."""
+    g = np.arange(24, dtype=np.float64) * 0.005
+    x = np.stack(np.meshgrid(0.4 + g, 0.4 + g, 0.4 + g, indexing="ij"), -1).reshape(-1, 3).astype(np.float32)
+    x = jitter(x, 0.005, seed=7)
+    ora, eng = _custom_pair(x)
+    # ~1900 neighbours per particle: the f32 summation order alone moves rho by ~2e-6 relative and
+    # the EOS raises it to the 7th power, so p gets 7 x the density tolerance in this stress case
+    # ... and the ~1900 cohesion terms of ~1 m/s^2 each cancel to |a| < g in the interior: the
+    # floor of the non-pressure comparison is the size of the partial sums, not |g|
+    run_stages(ora, eng, "summed", p_rtol=7 * RTOL, np_floor=200.0)
+    eng.close()
+
+
+def test_neighbour_list_overflow_falls_back():
+    """~1500 particles inside a ball of radius h/3 around a cell corner: the tile fits (<= 1792)
+    but every per-thread neighbour list overflows its 96 slots, so the force walk of those items
+    must come from the fallback kernel."""
+    rng = np.random.default_rng(11)
+    p = rng.normal(size=(1500, 3))
+    p *= (0.04 / 3) * rng.uniform(0, 1, size=(1500, 1)) ** (1 / 3) / np.linalg.norm(p, axis=1, keepdims=True)
+    x = (np.array([0.8, 0.8, 0.8]) + p).astype(np.float32)
+    ora, eng = _custom_pair(x)
+    run_stages(ora, eng, "summed", p_rtol=7 * RTOL)
+    eng.close()
+
+
+def test_sparse_cells():
+    """one to three particles per cell (spacing ~h): 32-lane items, mostly empty tiles."""
+    g = np.arange(12, dtype=np.float64) * 0.035
+    x = np.stack(np.meshgrid(0.3 + g, 0.3 + g, 0.3 + g, indexing="ij"), -1).reshape(-1, 3).astype(np.float32)
+    x = jitter(x, 0.035, seed=3)
+    ora, eng = _custom_pair(x)
+    run_stages(ora, eng, "summed")
     eng.close()
 
 

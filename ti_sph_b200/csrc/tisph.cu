@@ -11,6 +11,7 @@
 
 #include "tisph.h"
 #include "tisph_kernels.cuh"
+#include "tisph_walk.cuh"
 
 using namespace tisph;
 
@@ -58,6 +59,15 @@ struct tisph_ctx {
     int *cell_count = nullptr, *cell_end = nullptr, *block_sums = nullptr;
     int* color = nullptr;
     int* err_dev = nullptr;
+    // work items of the neighbour walks + neighbour lists handed from walk 1 to walk 2
+    int2* items = nullptr;
+    int items_cap = 0, list_items_cap = 0;
+    StepCounters* ctr = nullptr;
+    int *fb_d = nullptr, *fb_f = nullptr;
+    unsigned char* item_flags = nullptr;
+    uint2* Lg = nullptr;
+    unsigned short* Lcnt = nullptr;
+    int grid_dl = 0, grid_fl = 0, grid_dfb = 0, grid_ffb = 0;   // persistent grids (SMs x resident CTAs)
     void* staging = nullptr;
     size_t staging_bytes = 0;
     float4 *snapP = nullptr, *snapV = nullptr, *snapQ = nullptr;   // tisph_state_save
@@ -121,6 +131,7 @@ static int run_update(tisph_ctx* c) {
     int a = c->cur, b = c->cur ^ 1;
     int nb_cells = nblocks(c->ncell, SCAN_TILE);
     CU(cudaMemsetAsync(c->cell_count, 0, sizeof(int) * (size_t)c->ncell, st));
+    CU(cudaMemsetAsync(c->ctr, 0, sizeof(StepCounters), st));
     k_bin<<<nblocks(c->n, 256), 256, 0, st>>>(c->sp, c->P[a], c->keys, c->arrival, c->cell_count, c->err_dev);
     k_scan_reduce<<<nb_cells, SCAN_THREADS, 0, st>>>(c->cell_count, c->ncell, c->block_sums);
     k_scan_spine<<<1, 1024, 0, st>>>(c->block_sums, nb_cells);
@@ -128,7 +139,8 @@ static int run_update(tisph_ctx* c) {
     k_place<<<nblocks(c->n, 256), 256, 0, st>>>(c->n, c->keys, c->arrival, c->cell_end, c->ids);
     k_reorder<<<nblocks(c->n, 256), 256, 0, st>>>(c->n, c->keys, c->ids, c->cell_end, c->P[a], c->V[a],
                                                   c->Q[a], c->P[b], c->V[b], c->Q[b], c->keys_sorted);
-    c->launches += 6;
+    k_items<<<nblocks(c->ncell, 256), 256, 0, st>>>(c->ncell, c->cell_end, c->items, c->ctr);
+    c->launches += 7;
     CU(cudaGetLastError());
     c->cur = b;
     c->phase = 1;
@@ -139,13 +151,13 @@ static int run_update(tisph_ctx* c) {
 static int run_density(tisph_ctx* c) {
     if (c->phase != 1) return fail(TISPH_ERR_INVALID, "DENSITY issued out of order (phase %d)", c->phase);
     int b = c->cur;
-    if (c->variant == 1)
-        k_density<<<c->ncell, NB_THREADS, 0, c->stream>>>(c->sp, c->cell_end, c->P[b], c->V[b], c->Q[b],
-                                                          c->D, c->S, c->ncount);
-    else
-        k_density2<<<c->ncell, NB_THREADS, D2_SMEM, c->stream>>>(c->sp, c->cell_end, c->P[b], c->V[b],
-                                                                 c->Q[b], c->D, c->S, c->ncount);
-    c->launches += 1;
+    cudaStream_t st = c->stream;
+    k_density_list<<<c->grid_dl, NB_THREADS, DL_SMEM, st>>>(
+        c->sp, c->cell_end, c->items, c->ctr, c->list_items_cap, c->variant == 1, c->P[b], c->V[b], c->Q[b],
+        c->D, c->S, c->ncount, c->Lg, c->Lcnt, c->item_flags, c->fb_d, c->fb_f);
+    k_density_fb<<<c->grid_dfb, NB_THREADS, DF_SMEM, st>>>(c->sp, c->cell_end, c->items, c->ctr, c->fb_d,
+                                                          c->P[b], c->V[b], c->Q[b], c->D, c->S, c->ncount);
+    c->launches += 2;
     CU(cudaGetLastError());
     c->phase = 2;
     return TISPH_OK;
@@ -154,15 +166,16 @@ static int run_density(tisph_ctx* c) {
 static int run_force(tisph_ctx* c) {
     if (c->phase != 2) return fail(TISPH_ERR_INVALID, "FORCE_ADVECT issued out of order (phase %d)", c->phase);
     int b = c->cur, a = c->cur ^ 1;
+    cudaStream_t st = c->stream;
     float4* dnp = c->diagnostics ? c->a_np : nullptr;
     float4* dp = c->diagnostics ? c->a_p : nullptr;
-    if (c->variant == 1)
-        k_force<<<c->ncell, NB_THREADS, FORCE_SMEM, c->stream>>>(
-            c->sp, c->cell_end, c->P[b], c->V[b], c->Q[b], c->D, c->P[a], c->V[a], c->Q[a], c->dvel, dnp, dp);
-    else
-        k_force2<<<c->ncell, NB_THREADS, F2_SMEM, c->stream>>>(
-            c->sp, c->cell_end, c->P[b], c->V[b], c->Q[b], c->D, c->P[a], c->V[a], c->Q[a], c->dvel, dnp, dp);
-    c->launches += 1;
+    k_force_list<<<c->grid_fl, NB_THREADS, FL_SMEM, st>>>(
+        c->sp, c->cell_end, c->items, c->ctr, c->P[b], c->V[b], c->Q[b], c->D, c->P[a], c->V[a], c->Q[a],
+        c->dvel, dnp, dp, c->Lg, c->Lcnt, c->item_flags);
+    k_force_fb<<<c->grid_ffb, NB_THREADS, FF_SMEM, st>>>(
+        c->sp, c->cell_end, c->items, c->ctr, c->fb_f, c->P[b], c->V[b], c->Q[b], c->D, c->P[a], c->V[a],
+        c->Q[a], c->dvel, dnp, dp);
+    c->launches += 2;
     CU(cudaGetLastError());
     c->cur = a;
     c->phase = 0;
@@ -214,6 +227,18 @@ int tisph_create(const tisph_config* cfg, tisph_ctx** out) {
     A(dalloc(&c->block_sums, (size_t)nblocks(c->ncell, SCAN_TILE) + 1024));
     A(dalloc(&c->color, cap * 3));
     A(dalloc(&c->err_dev, 4));
+    {
+        int64_t occupied_max = ncell < (int64_t)cap ? ncell : (int64_t)cap;
+        c->items_cap = (int)(occupied_max + (int64_t)cap / 64 + 2);
+        int64_t budget = (int64_t)cap / 32 + 1024;           // items that get a neighbour list (48 KiB each)
+        c->list_items_cap = (int)(budget < c->items_cap ? budget : c->items_cap);
+    }
+    A(dalloc(&c->items, (size_t)c->items_cap));
+    A(dalloc(&c->ctr, 1));
+    A(dalloc(&c->fb_d, (size_t)c->items_cap)); A(dalloc(&c->fb_f, (size_t)c->items_cap));
+    A(dalloc(&c->item_flags, (size_t)c->items_cap));
+    A(dalloc(&c->Lg, (size_t)c->list_items_cap * ITEM_LIST_WORDS));
+    A(dalloc(&c->Lcnt, (size_t)c->list_items_cap * NB_THREADS));
     c->staging_bytes = cap * 16 * 3;
     A(cudaMalloc(&c->staging, c->staging_bytes));
     if (e == cudaSuccess) {
@@ -225,9 +250,20 @@ int tisph_create(const tisph_config* cfg, tisph_ctx** out) {
         A(cudaMemsetAsync(c->keys_sorted, 0, cap * 4, c->stream));
         A(cudaMemsetAsync(c->cell_end, 0, (size_t)c->ncell * 4, c->stream));
         A(cudaMemsetAsync(c->cell_count, 0, (size_t)c->ncell * 4, c->stream));
-        A(cudaFuncSetAttribute(k_force, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FORCE_SMEM));
-        A(cudaFuncSetAttribute(k_force2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F2_SMEM));
-        A(cudaFuncSetAttribute(k_density2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)D2_SMEM));
+        A(cudaFuncSetAttribute(k_density_list, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DL_SMEM));
+        A(cudaFuncSetAttribute(k_force_list, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FL_SMEM));
+        A(cudaFuncSetAttribute(k_density_fb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DF_SMEM));
+        A(cudaFuncSetAttribute(k_force_fb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FF_SMEM));
+        int sms = 0, occ = 0;
+        A(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg->device));
+        A(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_density_list, NB_THREADS, DL_SMEM));
+        c->grid_dl = sms * (occ > 0 ? occ : 1);
+        A(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_force_list, NB_THREADS, FL_SMEM));
+        c->grid_fl = sms * (occ > 0 ? occ : 1);
+        A(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_density_fb, NB_THREADS, DF_SMEM));
+        c->grid_dfb = sms * (occ > 0 ? occ : 1);
+        A(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_force_fb, NB_THREADS, FF_SMEM));
+        c->grid_ffb = sms * (occ > 0 ? occ : 1);
         A(cudaStreamSynchronize(c->stream));
     }
     if (e != cudaSuccess) {
@@ -249,6 +285,8 @@ int tisph_destroy(tisph_ctx* c) {
     cudaFree(c->keys_sorted); cudaFree(c->cell_count); cudaFree(c->cell_end);
     cudaFree(c->snapP); cudaFree(c->snapV); cudaFree(c->snapQ);
     cudaFree(c->block_sums); cudaFree(c->color); cudaFree(c->err_dev); cudaFree(c->staging);
+    cudaFree(c->items); cudaFree(c->ctr); cudaFree(c->fb_d); cudaFree(c->fb_f); cudaFree(c->item_flags);
+    cudaFree(c->Lg); cudaFree(c->Lcnt);
     if (c->ev_made)
         for (int s = 0; s < MAX_TIMED_STEPS; ++s)
             for (int k = 0; k < 4; ++k) cudaEventDestroy(c->ev[s][k]);

@@ -1,0 +1,600 @@
+// tisph_walk.cuh -- the two neighbour walks of a WCSPH step on sm_100a.
+//
+// Work items.  A walk is cut into ITEMS: one item = up to 64 target particles of one occupied
+// grid cell (k_items builds the list after the scan).  Persistent CTAs of 256 threads pull items
+// from an atomic counter, so the 97 % empty cells of a dam-break grid cost nothing.  Inside an
+// item the CTA's threads are arranged [split][target lane]: 32 or 64 targets, each walked by 8 or
+// 4 "split" threads that take interleaved 32-candidate chunks of the item's candidate tile; the
+// partial sums meet in shared memory.
+//
+// Candidate tile.  The 27 neighbour cells of a cell are 9 contiguous ranges of the sorted arrays
+// (z is the fastest key digit), staged into shared memory once per item.  Range of cell c is
+// [cell_end[max(0,c-1)], cell_end[c])  (partice_systemv4.py:343; cell 0 is therefore invisible as
+// a neighbour -- reference quirk, reproduced).  Cells outside the grid are empty (the reference
+// reads out of bounds there).
+//
+// Walk 1 (k_density_list): FILTER every candidate with packed f32x2 arithmetic (FADD2 / FMUL2 /
+// FFMA2: two candidates per instruction) against a cutoff widened by 1e-6 -- a superset of the
+// neighbours -- appending survivors to a per-thread pending list in shared memory ([slot][thread],
+// conflict free); DRAIN the lists on nearly full warps: exact IEEE test sqrt(d2) < h in the
+// reference's evaluation order (bit-exact neighbour set), kernel sum, count.  The drained lists
+// are also streamed to global memory (u16 tile indices, 4 per 8-byte word, [word][thread]).
+// Walk 2 (k_force_list): no filter at all -- every thread replays its list from global memory and
+// evaluates the pair forces; then advect + walls.  Items whose tile or list does not fit go
+// through the self-contained fallback kernels (k_density_fb / k_force_fb) instead.
+#pragma once
+#include "tisph_device.cuh"
+
+namespace tisph {
+
+constexpr int LCAP = 64;               // pending-list slots per thread (shared memory)
+constexpr int CHUNK = 32;              // candidates filtered between drain checks
+constexpr float FAR = 1e18f;           // padding candidates / idle targets: never within the cutoff
+constexpr int TCAP = 1792;             // candidates of one tile (27 cells x 64 at the reference spacing = 1728)
+constexpr int KCAP = 96;               // neighbour-list entries per thread and item in global memory
+constexpr int ITEM_LIST_WORDS = NB_THREADS * KCAP / 4;   // uint2 words of one item's lists
+
+struct StepCounters {
+    int n_items;        // built by k_items
+    int work_d, work_f; // work-stealing cursors of the list kernels
+    int n_fb_d, n_fb_f; // items handed to the fallback kernels
+    int work_fb_d, work_fb_f;
+    int pad;
+};
+
+// item = {cell, first target of the pass relative to the cell's first particle}
+__global__ void __launch_bounds__(256)
+k_items(int ncell, const int* __restrict__ cell_end, int2* __restrict__ items,
+        StepCounters* __restrict__ ctr) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    int cnt = 0;
+    if (c < ncell) cnt = cell_end[c] - cell_start(cell_end, c);
+    int ni = cnt == 0 ? 0 : (cnt + 63) >> 6;
+    // warp-aggregated reservation keeps the list roughly in cell order (L2 locality of the walks)
+    int lane = threadIdx.x & 31;
+    int inc = warp_inclusive_scan(ni, lane);
+    int tot = __shfl_sync(0xffffffffu, inc, 31);
+    int base = 0;
+    if (lane == 31 && tot > 0) base = atomicAdd(&ctr->n_items, tot);
+    base = __shfl_sync(0xffffffffu, base, 31) + inc - ni;
+    for (int k = 0; k < ni; ++k) items[base + k] = make_int2(c, k << 6);
+}
+
+struct ItemGeom {
+    int c, tb, te, i0, nT, tl, nsplit, total;
+};
+
+// ranges + geometry of one item; all threads must call (contains __syncthreads)
+__device__ __forceinline__ void item_setup(const SimParams& sp, const int* __restrict__ cell_end,
+                                           int2 item, CellRanges& R, ItemGeom& G) {
+    G.c = item.x;
+    G.tb = cell_start(cell_end, G.c);
+    G.te = cell_end[G.c];
+    G.i0 = G.tb + item.y;
+    G.nT = min(G.te - G.i0, 64);
+    G.tl = G.nT <= 32 ? 32 : 64;
+    G.nsplit = NB_THREADS / G.tl;
+    compute_cell_ranges(sp, cell_end, G.c, R);
+    G.total = R.off[9];
+}
+
+// ---- epilogues shared by the list and fallback kernels ------------------------------------
+// density / boundary volume / clamp + Tait EOS   (wcsphv2.py:28-34,45-47 ; sph_basev2.py:195-201)
+__device__ __forceinline__ void density_epilogue(const SimParams& sp, int i, float mass_i, int mat_i,
+                                                 float wsum, float wbsum, int cnt,
+                                                 float4* __restrict__ V, const float4* __restrict__ Q,
+                                                 float4* __restrict__ D, float* __restrict__ S,
+                                                 int* __restrict__ ncount) {
+    float rho_raw, s_i = 0.f;
+    if (mat_i == MAT_FLUID) {
+        float self = mass_i * sp.k_w;                  // mass_i * W(0)
+        s_i = mass_i * (sp.k_w * wsum);                // sum_j mass_i W(r_ij)   (Q2)
+        rho_raw = sp.density_mode == 1 ? self + s_i : self;
+    } else {
+        rho_raw = Q[i].x;                              // boundary keeps its stored density
+        float delta = sp.k_w + (sp.volume_mode == 1 ? sp.k_w * wbsum : 0.f);   // sph_basev2.py:195-201
+        float4 vi = V[i];
+        vi.w = 1.0f / delta;
+        V[i] = vi;
+    }
+    float rho_c = fmaxf(rho_raw, sp.rho0);                                                       // :46
+    float pr = sp.stiffness * (eos_pow(rho_c / sp.rho0, sp.exponent, sp.int_exponent) - 1.0f);   // :47
+    D[i] = make_float4(rho_raw, pr / (rho_c * rho_c), rho_c, pr);
+    S[i] = s_i;
+    ncount[i] = cnt;
+}
+
+// a = g - non-pressure sums + pressure sums; advert; walls
+// (wcsphv2.py:89-93, :53, :95-100 ; sph_basev2.py:151-189)
+__device__ __forceinline__ void force_epilogue(const SimParams& sp, int i, bool walker, float4 pi, float4 vi,
+                                               float4 di, float4 qi, float anx, float any, float anz,
+                                               float apx, float apy, float apz,
+                                               float4* __restrict__ Pout, float4* __restrict__ Vout,
+                                               float4* __restrict__ Qout, float4* __restrict__ dvel,
+                                               float4* __restrict__ a_np_out, float4* __restrict__ a_p_out) {
+    float4 pout = pi, vout = vi, acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (walker) {
+        float nx = sp.g[0] - anx, ny = sp.g[1] - any, nz = sp.g[2] - anz;
+        if (a_np_out) {
+            a_np_out[i] = make_float4(nx, ny, nz, 0.f);
+            a_p_out[i] = make_float4(apx, apy, apz, 0.f);
+        }
+        acc.x = nx + apx; acc.y = ny + apy; acc.z = nz + apz;
+        vout.x = vi.x + sp.dt * acc.x; vout.y = vi.y + sp.dt * acc.y; vout.z = vi.z + sp.dt * acc.z;
+        float px = pi.x + sp.dt * vout.x, py = pi.y + sp.dt * vout.y, pz = pi.z + sp.dt * vout.z;
+        float cnx = 0.f, cny = 0.f, cnz = 0.f;       // the wall tests use the pre-clamp position
+        pout.x = px; pout.y = py; pout.z = pz;
+        if (px > sp.wall_hi[0]) { cnx += 1.f; pout.x = sp.wall_hi[0]; }
+        if (px <= sp.pad)       { cnx -= 1.f; pout.x = sp.pad; }
+        if (py > sp.wall_hi[1]) { cny += 1.f; pout.y = sp.wall_hi[1]; }
+        if (py <= sp.pad)       { cny -= 1.f; pout.y = sp.pad; }
+        if (pz > sp.wall_hi[2]) { cnz += 1.f; pout.z = sp.wall_hi[2]; }
+        if (pz <= sp.pad)       { cnz -= 1.f; pout.z = sp.pad; }
+        float len = sqrtf(cnx * cnx + cny * cny + cnz * cnz);
+        if (len > 1e-6f) {
+            float ux = cnx / len, uy = cny / len, uz = cnz / len;
+            float sdot = 1.5f * (vout.x * ux + vout.y * uy + vout.z * uz);   // :151-156
+            vout.x -= sdot * ux; vout.y -= sdot * uy; vout.z -= sdot * uz;
+        }
+    } else if (a_np_out) {
+        a_np_out[i] = acc;
+        a_p_out[i] = acc;
+    }
+    Pout[i] = pout;
+    Vout[i] = vout;
+    Qout[i] = make_float4(di.z, di.w, qi.z, qi.w);     // clamped rho, p, material, orig id
+    dvel[i] = acc;
+}
+
+// pair forces of one accepted neighbour (wcsphv2.py:56-80 ; sph_basev2.py:64-78)
+//   pj = {x,y,z,psi}: psi = +mass_j (fluid j) / -volume_j (boundary j);  vj = {vx,vy,vz,rho_raw_j}
+struct ForceAcc { float anx, any, anz, apx, apy, apz; };
+
+__device__ __forceinline__ void pair_force(const SimParams& sp, float dx, float dy, float dz, float d2,
+                                           float4 vi, float psi, float4 vj, float prj, float coh_i,
+                                           float rho_i, float pr_i, float nub_i, ForceAcc& A) {
+    float rinv = rsqrtf(fmaxf(d2, 1e-30f));
+    float r = d2 * rinv;
+    float q = r * sp.inv_h;
+    // gradW = k_dw dw(q) x_ij / (r h); zero for r <= 1e-5 (sph_basev2.py:53)
+    float gfac = r > 1e-5f ? sp.k_dw * spline_dw(q) * rinv * sp.inv_h : 0.f;
+    float dot = (vi.x - vj.x) * dx + (vi.y - vj.y) * dy + (vi.z - vj.z) * dz;
+    float mn = fminf(dot, 0.f) * fast_rcp(d2 + sp.eps_h2);
+    float cn, cp;
+    if (psi > 0.f) {                                                   // fluid j
+        float w = sp.k_w * spline_w(q);
+        float nu = sp.visc_fluid_c * fast_rcp(rho_i + vj.w);           // wcsphv2.py:69
+        cn = psi * (coh_i * w - nu * mn * gfac);                       // :64 + :72-73
+        cp = -psi * (pr_i + prj) * gfac;                               // sph_basev2.py:71-73
+    } else {                                                           // boundary j
+        float vol = -psi;
+        cn = sp.ps_density0 * vol * (-nub_i * mn) * gfac;              // wcsphv2.py:78-80
+        cp = -sp.rho0 * vol * pr_i * gfac;                             // sph_basev2.py:75
+    }
+    A.anx = fmaf(cn, dx, A.anx); A.any = fmaf(cn, dy, A.any); A.anz = fmaf(cn, dz, A.anz);
+    A.apx = fmaf(cp, dx, A.apx); A.apy = fmaf(cp, dy, A.apy); A.apz = fmaf(cp, dz, A.apz);
+}
+
+__device__ __forceinline__ int next_item(int* cursor, int* s_slot) {
+    __syncthreads();                       // everyone is done with the previous item's shared state
+    if (threadIdx.x == 0) *s_slot = atomicAdd(cursor, 1);
+    __syncthreads();
+    return *s_slot;
+}
+
+// =======================================================================================
+// Walk 1, list path
+// =======================================================================================
+// tile (pair-SoA, NEGATED coordinates so that x_i - x_j is one packed add):
+//   txy[p] = {-x(2p), -x(2p+1), -y(2p), -y(2p+1)}   tz[p] = {-z(2p), -z(2p+1)}   tm[e] = material
+constexpr size_t DL_SMEM = (size_t)(TCAP / 2) * (sizeof(float4) + sizeof(float2)) + (size_t)TCAP * sizeof(int) +
+                           (size_t)LCAP * NB_THREADS * sizeof(unsigned short);
+
+__global__ void __launch_bounds__(NB_THREADS, 3)
+k_density_list(SimParams sp, const int* __restrict__ cell_end, const int2* __restrict__ items,
+               StepCounters* __restrict__ ctr, int list_items_cap, int all_to_fallback,
+               const float4* __restrict__ P, float4* __restrict__ V, const float4* __restrict__ Q,
+               float4* __restrict__ D, float* __restrict__ S, int* __restrict__ ncount,
+               uint2* __restrict__ Lg, unsigned short* __restrict__ Lcnt, unsigned char* __restrict__ flags,
+               int* __restrict__ fb_d, int* __restrict__ fb_f) {
+    extern __shared__ float4 dyn_smem[];
+    float4* txy = dyn_smem;
+    float2* tz = reinterpret_cast<float2*>(dyn_smem + TCAP / 2);
+    int* tm = reinterpret_cast<int*>(tz + TCAP / 2);
+    unsigned short* L = reinterpret_cast<unsigned short*>(tm + TCAP);
+    const float* fxy = reinterpret_cast<const float*>(txy);
+    const float* fz = reinterpret_cast<const float*>(tz);
+    __shared__ CellRanges R;
+    __shared__ float red_w[NB_THREADS];
+    __shared__ float red_b[NB_THREADS];
+    __shared__ int red_c[NB_THREADS];
+    __shared__ int s_slot, s_over;
+
+    const int tid = threadIdx.x;
+    const bool akinci = sp.volume_mode == 1;
+    const float cut_wide = sp.d2_cut * 1.000001f;       // superset filter; the drain applies the exact test
+    unsigned short* myL = L + tid;
+
+    for (;;) {
+        const int it = next_item(&ctr->work_d, &s_slot);
+        if (it >= ctr->n_items) break;
+        ItemGeom G;
+        item_setup(sp, cell_end, items[it], R, G);
+        if (G.total > TCAP || all_to_fallback) {        // tile does not fit: self-contained fallback kernels
+            if (tid == 0) {
+                flags[it] = 2;
+                fb_d[atomicAdd(&ctr->n_fb_d, 1)] = it;
+                fb_f[atomicAdd(&ctr->n_fb_f, 1)] = it;
+            }
+            continue;
+        }
+        const bool keep_list = it < list_items_cap;
+        if (tid == 0) s_over = keep_list ? 0 : 1;
+        // ---- stage the tile ---------------------------------------------------------------
+        const int nchunk = (G.total + CHUNK - 1) / CHUNK;
+        for (int p = tid; p < nchunk * (CHUNK / 2); p += NB_THREADS) {
+            float4 a = make_float4(FAR, FAR, FAR, 0.f), b = a;
+            int ma = MAT_FLUID, mb = MAT_FLUID;
+            int e = 2 * p;
+            if (e < G.total) {
+                int g = tile_to_global(R, e);
+                a = P[g];
+                if (akinci) ma = __float_as_int(Q[g].z);
+            }
+            if (e + 1 < G.total) {
+                int g = tile_to_global(R, e + 1);
+                b = P[g];
+                if (akinci) mb = __float_as_int(Q[g].z);
+            }
+            txy[p] = make_float4(-a.x, -b.x, -a.y, -b.y);
+            tz[p] = make_float2(-a.z, -b.z);
+            *reinterpret_cast<int2*>(tm + e) = make_int2(ma, mb);
+        }
+        __syncthreads();
+        // ---- walk -------------------------------------------------------------------------
+        const int t_local = tid % G.tl, split = tid / G.tl;
+        const int i = G.i0 + t_local;
+        const bool active = t_local < G.nT;
+        const float4 pi = active ? P[i] : make_float4(-FAR, -FAR, -FAR, 0.f);
+        const int self_lo = R.gb[4], self_len = R.off[5] - R.off[4];
+        const int self_t = (active && i >= self_lo && i < self_lo + self_len) ? R.off[4] + (i - self_lo) : -1;
+        const float2 xi2 = make_float2(pi.x, pi.x), yi2 = make_float2(pi.y, pi.y), zi2 = make_float2(pi.z, pi.z);
+        float wsum = 0.f, wbsum = 0.f;
+        int cnt = 0, pend = 0, goff = 0;
+        unsigned short* gl = reinterpret_cast<unsigned short*>(Lg + (size_t)it * ITEM_LIST_WORDS);
+        for (int ch = split; ch < nchunk; ch += G.nsplit) {
+            const int pb = ch * (CHUNK / 2);
+#pragma unroll 8
+            for (int k = 0; k < CHUNK / 2; ++k) {
+                float4 c = txy[pb + k];
+                float2 cz = tz[pb + k];
+                float2 dx = __fadd2_rn(xi2, make_float2(c.x, c.y));
+                float2 dy = __fadd2_rn(yi2, make_float2(c.z, c.w));
+                float2 dz = __fadd2_rn(zi2, cz);
+                float2 s = __ffma2_rn(dz, dz, __ffma2_rn(dy, dy, __fmul2_rn(dx, dx)));
+                if (s.x < cut_wide) { myL[pend * NB_THREADS] = (unsigned short)(2 * (pb + k)); ++pend; }
+                if (s.y < cut_wide) { myL[pend * NB_THREADS] = (unsigned short)(2 * (pb + k) + 1); ++pend; }
+            }
+            const bool last = ch + G.nsplit >= nchunk;
+            if (last || __any_sync(0xffffffffu, pend > LCAP - CHUNK)) {
+                for (int k = 0; k < pend; ++k) {
+                    const int e = myL[k * NB_THREADS];
+                    const int o = ((e >> 1) << 2) + (e & 1);
+                    const float dx = pi.x + fxy[o], dy = pi.y + fxy[o + 2], dz = pi.z + fz[e];
+                    const float d2 = dist2_exact(dx, dy, dz);
+                    if (keep_list && goff + k < KCAP) {
+                        const int kk = goff + k;       // [word kk/4][thread][kk%4]
+                        gl[((size_t)(kk >> 2) * NB_THREADS + tid) * 4 + (kk & 3)] = (unsigned short)e;
+                    }
+                    if (d2 < sp.d2_cut && e != self_t) {
+                        float r = d2 * rsqrtf(fmaxf(d2, 1e-30f));
+                        float w = spline_w(r * sp.inv_h);
+                        cnt++;
+                        wsum += w;
+                        if (tm[e] == MAT_BOUNDARY) wbsum += w;
+                    }
+                }
+                goff += pend;
+                pend = 0;
+            }
+        }
+        if (keep_list) {
+            Lcnt[(size_t)it * NB_THREADS + tid] = (unsigned short)min(goff, KCAP);
+            if (goff > KCAP) s_over = 1;               // benign race: every writer stores 1
+        }
+        red_w[tid] = wsum;
+        red_b[tid] = wbsum;
+        red_c[tid] = cnt;
+        __syncthreads();
+        if (tid == 0) {
+            flags[it] = (unsigned char)s_over;
+            if (s_over) fb_f[atomicAdd(&ctr->n_fb_f, 1)] = it;
+        }
+        if (split == 0 && active) {
+            for (int s = 1; s < G.nsplit; ++s) {
+                wsum += red_w[s * G.tl + t_local];
+                wbsum += red_b[s * G.tl + t_local];
+                cnt += red_c[s * G.tl + t_local];
+            }
+            density_epilogue(sp, i, pi.w, __float_as_int(Q[i].z), wsum, wbsum, cnt, V, Q, D, S, ncount);
+        }
+    }
+}
+
+// =======================================================================================
+// Walk 2, list path: forces + advect + walls
+//   tile record, 36 B per candidate: tP = {x,y,z,psi}  tV = {vx,vy,vz,rho_raw}  tR = p/rho_c^2
+// =======================================================================================
+constexpr size_t FL_SMEM = (size_t)TCAP * (2 * sizeof(float4) + sizeof(float));
+
+__device__ __forceinline__ void stage_force_tile(const CellRanges& R, int tile0, int tile_n, int tile_pad,
+                                                 const float4* __restrict__ Pin, const float4* __restrict__ Vin,
+                                                 const float4* __restrict__ Qin, const float4* __restrict__ D,
+                                                 float4* tP, float4* tV, float* tR) {
+    for (int e = threadIdx.x; e < tile_pad; e += NB_THREADS) {
+        float4 p = make_float4(FAR, FAR, FAR, 0.f), v = make_float4(0.f, 0.f, 0.f, 1.f);
+        float pr = 0.f;
+        if (e < tile_n) {
+            int g = tile_to_global(R, tile0 + e);
+            p = Pin[g];
+            v = Vin[g];
+            float4 d = D[g];
+            if (__float_as_int(Qin[g].z) != MAT_FLUID) p.w = -v.w;   // psi = -volume
+            v.w = d.x;
+            pr = d.y;
+        }
+        tP[e] = p; tV[e] = v; tR[e] = pr;
+    }
+}
+
+__global__ void __launch_bounds__(NB_THREADS, 3)
+k_force_list(SimParams sp, const int* __restrict__ cell_end, const int2* __restrict__ items,
+             StepCounters* __restrict__ ctr, const float4* __restrict__ Pin,
+             const float4* __restrict__ Vin, const float4* __restrict__ Qin,
+             const float4* __restrict__ D, float4* __restrict__ Pout, float4* __restrict__ Vout,
+             float4* __restrict__ Qout, float4* __restrict__ dvel, float4* __restrict__ a_np_out,
+             float4* __restrict__ a_p_out, const uint2* __restrict__ Lg,
+             const unsigned short* __restrict__ Lcnt, const unsigned char* __restrict__ flags) {
+    extern __shared__ float4 dyn_smem[];
+    float4* tP = dyn_smem;
+    float4* tV = dyn_smem + TCAP;
+    float* tR = reinterpret_cast<float*>(dyn_smem + 2 * TCAP);
+    __shared__ CellRanges R;
+    __shared__ float red[6][NB_THREADS];
+    __shared__ int s_slot;
+    const int tid = threadIdx.x;
+
+    for (;;) {
+        const int it = next_item(&ctr->work_f, &s_slot);
+        if (it >= ctr->n_items) break;
+        if (flags[it]) continue;                         // handled by k_force_fb
+        ItemGeom G;
+        item_setup(sp, cell_end, items[it], R, G);
+        stage_force_tile(R, 0, G.total, G.total, Pin, Vin, Qin, D, tP, tV, tR);
+        const int t_local = tid % G.tl, split = tid / G.tl;
+        const int i = G.i0 + t_local;
+        const bool active = t_local < G.nT;
+        const float4 pi = active ? Pin[i] : make_float4(-FAR, -FAR, -FAR, 1.f);
+        const float4 vi = active ? Vin[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 di = active ? D[i] : make_float4(1.f, 0.f, 1.f, 0.f);
+        const float4 qi = active ? Qin[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+        const bool walker = active && __float_as_int(qi.z) == MAT_FLUID && i >= sp.owned_lo && i < sp.owned_hi;
+        const int self_lo = R.gb[4], self_len = R.off[5] - R.off[4];
+        const int self_t = (active && i >= self_lo && i < self_lo + self_len) ? R.off[4] + (i - self_lo) : -1;
+        const float coh_i = 0.01f / pi.w;                         // wcsphv2.py:64
+        const float rho_i = di.x, pr_i = di.y;
+        const float nub_i = sp.visc_bound_c / (2.0f * rho_i);     // wcsphv2.py:76
+        ForceAcc A = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        const int cnt = walker ? (int)Lcnt[(size_t)it * NB_THREADS + tid] : 0;
+        const uint2* gl = Lg + (size_t)it * ITEM_LIST_WORDS + tid;
+        __syncthreads();                                   // tile staged
+        uint2 w = cnt > 0 ? gl[0] : make_uint2(0u, 0u);
+        for (int k4 = 0; k4 < cnt; k4 += 4) {
+            const uint2 cur = w;
+            if (k4 + 4 < cnt) w = gl[(size_t)((k4 >> 2) + 1) * NB_THREADS];     // prefetch the next 4 entries
+            const int e4[4] = {(int)(cur.x & 0xffffu), (int)(cur.x >> 16), (int)(cur.y & 0xffffu), (int)(cur.y >> 16)};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int e = e4[j];
+                if (k4 + j < cnt) {
+                    const float4 pj = tP[e];
+                    const float dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
+                    const float d2 = dist2_exact(dx, dy, dz);
+                    if (d2 < sp.d2_cut && e != self_t)
+                        pair_force(sp, dx, dy, dz, d2, vi, pj.w, tV[e], tR[e], coh_i, rho_i, pr_i, nub_i, A);
+                }
+            }
+        }
+        red[0][tid] = A.anx; red[1][tid] = A.any; red[2][tid] = A.anz;
+        red[3][tid] = A.apx; red[4][tid] = A.apy; red[5][tid] = A.apz;
+        __syncthreads();
+        if (split == 0 && active) {
+            for (int s = 1; s < G.nsplit; ++s) {
+                int o = s * G.tl + t_local;
+                A.anx += red[0][o]; A.any += red[1][o]; A.anz += red[2][o];
+                A.apx += red[3][o]; A.apy += red[4][o]; A.apz += red[5][o];
+            }
+            force_epilogue(sp, i, walker, pi, vi, di, qi, A.anx, A.any, A.anz, A.apx, A.apy, A.apz,
+                           Pout, Vout, Qout, dvel, a_np_out, a_p_out);
+        }
+    }
+}
+
+// =======================================================================================
+// Fallback kernels: any tile size (multi-tile loop), scalar exact filter, no global lists.
+// They run over the (normally empty) fallback item lists.
+// =======================================================================================
+constexpr size_t DF_SMEM = (size_t)TCAP * sizeof(float4) + (size_t)LCAP * NB_THREADS * sizeof(unsigned short);
+
+__global__ void __launch_bounds__(NB_THREADS, 3)
+k_density_fb(SimParams sp, const int* __restrict__ cell_end, const int2* __restrict__ items,
+             StepCounters* __restrict__ ctr, const int* __restrict__ fb_d, const float4* __restrict__ P,
+             float4* __restrict__ V, const float4* __restrict__ Q, float4* __restrict__ D,
+             float* __restrict__ S, int* __restrict__ ncount) {
+    extern __shared__ float4 dyn_smem[];
+    float4* tile = dyn_smem;                                           // {x,y,z,material}
+    unsigned short* L = reinterpret_cast<unsigned short*>(dyn_smem + TCAP);
+    __shared__ CellRanges R;
+    __shared__ float red_w[NB_THREADS];
+    __shared__ float red_b[NB_THREADS];
+    __shared__ int red_c[NB_THREADS];
+    __shared__ int s_slot;
+    const int tid = threadIdx.x;
+    const bool akinci = sp.volume_mode == 1;
+    unsigned short* myL = L + tid;
+
+    for (;;) {
+        const int w = next_item(&ctr->work_fb_d, &s_slot);
+        if (w >= ctr->n_fb_d) break;
+        const int it = fb_d[w];
+        ItemGeom G;
+        item_setup(sp, cell_end, items[it], R, G);
+        const int t_local = tid % G.tl, split = tid / G.tl;
+        const int i = G.i0 + t_local;
+        const bool active = t_local < G.nT;
+        const float4 pi = active ? P[i] : make_float4(-FAR, -FAR, -FAR, 0.f);
+        const int self_lo = R.gb[4], self_len = R.off[5] - R.off[4];
+        const int self_e = (active && i >= self_lo && i < self_lo + self_len) ? R.off[4] + (i - self_lo) : -1;
+        float wsum = 0.f, wbsum = 0.f;
+        int cnt = 0;
+        for (int tile0 = 0; tile0 < G.total; tile0 += TCAP) {
+            const int tile_n = min(TCAP, G.total - tile0);
+            const int tile_pad = (tile_n + CHUNK - 1) & ~(CHUNK - 1);
+            __syncthreads();
+            for (int e = tid; e < tile_pad; e += NB_THREADS) {
+                float4 p = make_float4(FAR, FAR, FAR, 0.f);
+                if (e < tile_n) {
+                    int g = tile_to_global(R, tile0 + e);
+                    p = P[g];
+                    p.w = akinci ? Q[g].z : 0.f;
+                }
+                tile[e] = p;
+            }
+            __syncthreads();
+            const int self_t = self_e - tile0;
+            int pend = 0;
+            for (int cb = split * CHUNK; cb < tile_pad; cb += G.nsplit * CHUNK) {
+#pragma unroll 8
+                for (int k = 0; k < CHUNK; ++k) {
+                    float4 cj = tile[cb + k];
+                    float d2 = dist2_exact(pi.x - cj.x, pi.y - cj.y, pi.z - cj.z);
+                    if (d2 < sp.d2_cut) { myL[pend * NB_THREADS] = (unsigned short)(cb + k); ++pend; }
+                }
+                const bool last = cb + G.nsplit * CHUNK >= tile_pad;
+                if (last || __any_sync(0xffffffffu, pend > LCAP - CHUNK)) {
+                    for (int k = 0; k < pend; ++k) {
+                        int e = myL[k * NB_THREADS];
+                        if (e == self_t) continue;
+                        float4 cj = tile[e];
+                        float d2 = dist2_exact(pi.x - cj.x, pi.y - cj.y, pi.z - cj.z);
+                        float r = d2 * rsqrtf(fmaxf(d2, 1e-30f));
+                        float wv = spline_w(r * sp.inv_h);
+                        cnt++;
+                        wsum += wv;
+                        if (__float_as_int(cj.w) == MAT_BOUNDARY) wbsum += wv;
+                    }
+                    pend = 0;
+                }
+            }
+        }
+        red_w[tid] = wsum;
+        red_b[tid] = wbsum;
+        red_c[tid] = cnt;
+        __syncthreads();
+        if (split == 0 && active) {
+            for (int s = 1; s < G.nsplit; ++s) {
+                wsum += red_w[s * G.tl + t_local];
+                wbsum += red_b[s * G.tl + t_local];
+                cnt += red_c[s * G.tl + t_local];
+            }
+            density_epilogue(sp, i, pi.w, __float_as_int(Q[i].z), wsum, wbsum, cnt, V, Q, D, S, ncount);
+        }
+    }
+}
+
+constexpr size_t FF_SMEM = FL_SMEM + (size_t)LCAP * NB_THREADS * sizeof(unsigned short);
+
+__global__ void __launch_bounds__(NB_THREADS, 2)
+k_force_fb(SimParams sp, const int* __restrict__ cell_end, const int2* __restrict__ items,
+           StepCounters* __restrict__ ctr, const int* __restrict__ fb_f, const float4* __restrict__ Pin,
+           const float4* __restrict__ Vin, const float4* __restrict__ Qin,
+           const float4* __restrict__ D, float4* __restrict__ Pout, float4* __restrict__ Vout,
+           float4* __restrict__ Qout, float4* __restrict__ dvel, float4* __restrict__ a_np_out,
+           float4* __restrict__ a_p_out) {
+    extern __shared__ float4 dyn_smem[];
+    float4* tP = dyn_smem;
+    float4* tV = dyn_smem + TCAP;
+    float* tR = reinterpret_cast<float*>(dyn_smem + 2 * TCAP);
+    unsigned short* L = reinterpret_cast<unsigned short*>(tR + TCAP);
+    __shared__ CellRanges R;
+    __shared__ float red[6][NB_THREADS];
+    __shared__ int s_slot;
+    const int tid = threadIdx.x;
+    unsigned short* myL = L + tid;
+
+    for (;;) {
+        const int wk = next_item(&ctr->work_fb_f, &s_slot);
+        if (wk >= ctr->n_fb_f) break;
+        const int it = fb_f[wk];
+        ItemGeom G;
+        item_setup(sp, cell_end, items[it], R, G);
+        const int t_local = tid % G.tl, split = tid / G.tl;
+        const int i = G.i0 + t_local;
+        const bool active = t_local < G.nT;
+        const float4 pi = active ? Pin[i] : make_float4(-FAR, -FAR, -FAR, 1.f);
+        const float4 vi = active ? Vin[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 di = active ? D[i] : make_float4(1.f, 0.f, 1.f, 0.f);
+        const float4 qi = active ? Qin[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+        const bool walker = active && __float_as_int(qi.z) == MAT_FLUID && i >= sp.owned_lo && i < sp.owned_hi;
+        const float xi = walker ? pi.x : -FAR, yi = walker ? pi.y : -FAR, zi = walker ? pi.z : -FAR;
+        const int self_lo = R.gb[4], self_len = R.off[5] - R.off[4];
+        const int self_e = (active && i >= self_lo && i < self_lo + self_len) ? R.off[4] + (i - self_lo) : -1;
+        const float coh_i = 0.01f / pi.w;
+        const float rho_i = di.x, pr_i = di.y;
+        const float nub_i = sp.visc_bound_c / (2.0f * rho_i);
+        ForceAcc A = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        for (int tile0 = 0; tile0 < G.total; tile0 += TCAP) {
+            const int tile_n = min(TCAP, G.total - tile0);
+            const int tile_pad = (tile_n + CHUNK - 1) & ~(CHUNK - 1);
+            __syncthreads();
+            stage_force_tile(R, tile0, tile_n, tile_pad, Pin, Vin, Qin, D, tP, tV, tR);
+            __syncthreads();
+            const int self_t = self_e - tile0;
+            int pend = 0;
+            for (int cb = split * CHUNK; cb < tile_pad; cb += G.nsplit * CHUNK) {
+#pragma unroll 8
+                for (int k = 0; k < CHUNK; ++k) {
+                    float4 pj = tP[cb + k];
+                    float d2 = dist2_exact(xi - pj.x, yi - pj.y, zi - pj.z);
+                    if (d2 < sp.d2_cut) { myL[pend * NB_THREADS] = (unsigned short)(cb + k); ++pend; }
+                }
+                const bool last = cb + G.nsplit * CHUNK >= tile_pad;
+                if (last || __any_sync(0xffffffffu, pend > LCAP - CHUNK)) {
+                    for (int k = 0; k < pend; ++k) {
+                        int e = myL[k * NB_THREADS];
+                        if (e == self_t) continue;
+                        float4 pj = tP[e];
+                        float dx = xi - pj.x, dy = yi - pj.y, dz = zi - pj.z;
+                        float d2 = dist2_exact(dx, dy, dz);
+                        pair_force(sp, dx, dy, dz, d2, vi, pj.w, tV[e], tR[e], coh_i, rho_i, pr_i, nub_i, A);
+                    }
+                    pend = 0;
+                }
+            }
+        }
+        red[0][tid] = A.anx; red[1][tid] = A.any; red[2][tid] = A.anz;
+        red[3][tid] = A.apx; red[4][tid] = A.apy; red[5][tid] = A.apz;
+        __syncthreads();
+        if (split == 0 && active) {
+            for (int s = 1; s < G.nsplit; ++s) {
+                int o = s * G.tl + t_local;
+                A.anx += red[0][o]; A.any += red[1][o]; A.anz += red[2][o];
+                A.apx += red[3][o]; A.apy += red[4][o]; A.apz += red[5][o];
+            }
+            force_epilogue(sp, i, walker, pi, vi, di, qi, A.anx, A.any, A.anz, A.apx, A.apy, A.apz,
+                           Pout, Vout, Qout, dvel, a_np_out, a_p_out);
+        }
+    }
+}
+
+}  // namespace tisph
