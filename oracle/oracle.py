@@ -55,6 +55,12 @@ def lib():
     return _LIB
 
 
+def set_pow_mode(mode):
+    """0: q**3 by repeated multiplication (Taichi's lowering; default).  1: libm powf, the way
+    numpy evaluates `**` under the Taichi stand-in that produced tests/golden/ (bit-comparable)."""
+    lib().ora_set_pow_mode(int(mode))
+
+
 def _p(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 
@@ -85,7 +91,7 @@ class Gen2Oracle:
     """ParticleSystemV4 + WCSPHV2 on the CPU."""
 
     def __init__(self, scene, density_mode="reference", volume_mode="reference",
-                 boundary_points=None, threads=None):
+                 boundary_points=None, threads=None, boundary_color=(255, 255, 255)):
         cfg = scene["configuration"]
         self.dim = cfg["dim"]
         assert self.dim == 3
@@ -144,8 +150,12 @@ class Gen2Oracle:
             mats.append(np.ones(len(pos), np.int32))
         self.set_state(np.concatenate(xs), np.concatenate(vs), np.concatenate(ds),
                        np.concatenate(mats))
+        # rigid colours: ints are divided by 255.0 and the f32 result is cast back into the i32
+        # colour field (:111-114,190), so [255,255,255] is stored as (1,1,1)
+        bc = [c / 255.0 if type(boundary_color[0]) == int else c for c in boundary_color]
+        self.color[self.material == 0] = np.array(bc, np.float32).astype(np.int32)
 
-    def set_state(self, x, v, density, material, pressure=None, volume=None, mass=None):
+    def set_state(self, x, v, density, material, pressure=None, volume=None, mass=None, color=None):
         n = len(x)
         self.n = n
         self.x = _f32(x).copy(); self.v = _f32(v).copy()
@@ -155,8 +165,11 @@ class Gen2Oracle:
         self.volume = (np.full(n, self.m_V0, np.float32) if volume is None
                        else _f32(volume).copy())                        # :203
         self.mass = (self.volume * self.density if mass is None else _f32(mass).copy())  # :204
-        self.color = np.zeros((n, 3), np.int32)
-        self.color[self.material == 1] = 0x111111                      # :144 (scalar -> every lane)
+        if color is None:
+            self.color = np.zeros((n, 3), np.int32)
+            self.color[self.material == 1] = 0x111111                  # :144 (scalar -> every lane)
+        else:
+            self.color = np.ascontiguousarray(color, np.int32).reshape(n, 3).copy()
         self.m = np.zeros(n, np.float32)
         self.orig = np.arange(n, dtype=np.int32)      # bookkeeping only (not a reference field)
         self.keys = np.zeros(n, np.int32)

@@ -83,18 +83,31 @@ void ora_set_num_threads(int n) {
 
 /* ---------------------------------------------------------------- kernels */
 
+/* How `q ** 3` and `(1 - q) ** 3` (sph_basev2.py:33,35) are evaluated.
+ *   0 (default): repeated multiplication -- Taichi's alg_simp pass lowers pow(x, small
+ *                integer constant) to multiplications;
+ *   1          : libm powf (also for `** 2`), which is how numpy evaluates `**` when the reference sources run
+ *                on the Taichi stand-in that produced tests/golden/ (bit-comparable mode). */
+static int g_pow_mode = 0;
+void ora_set_pow_mode(int m) { g_pow_mode = m; }
+/* volatile exponents: gcc would otherwise fold powf(x, 2.0f) into x * x, which differs from
+ * libm's powf in the last bit for ~0.07 % of the arguments */
+static volatile float g_two = 2.0f, g_three = 3.0f;
+static inline float cube(float x) { return g_pow_mode ? powf(x, g_three) : (x * x) * x; }
+static inline float sq(float x) { return g_pow_mode ? powf(x, g_two) : x * x; }
+
 /* sph_basev2.py:19-36 / sph_base.py:18-35 */
 static inline float cubic_kernel(const ora_config *c, float r_norm) {
     float res = 0.0f;
     float q = r_norm / c->h;
     if (q <= 1.0f) {
         if (q <= 0.5f) {
-            float q2 = q * q;
-            float q3 = q2 * q;
+            float q2 = sq(q);
+            float q3 = cube(q);
             res = c->k_w * (6.0f * (q3 - q2) + 1.0f);
         } else {
             float f = 1.0f - q;
-            res = (c->k_w * 2.0f) * ((f * f) * f);
+            res = (c->k_w * 2.0f) * cube(f);
         }
     }
     return res;
@@ -325,13 +338,13 @@ void ora_pressure_force(const ora_config *c, int n, const float *x, const float 
     for (int i = 0; i < n; ++i) {
         if (material[i] != MAT_FLUID) continue;
         float d[3] = {0.0f, 0.0f, 0.0f};
-        float p_rho_i = pressure[i] / (density[i] * density[i]);
+        float p_rho_i = pressure[i] / sq(density[i]);
         FOR_ALL_NEIGHBORS3(c, scan, x, i, j, {
             float gw[3];
             cubic_kernel_derivative(c, r_, gw);
             if (material[j] == MAT_FLUID) {
-                float s = -mass[j] * (pressure[i] / (density[i] * density[i]) +
-                                      pressure[j] / (density[j] * density[j]));
+                float s = -mass[j] * (pressure[i] / sq(density[i]) +
+                                      pressure[j] / sq(density[j]));
                 for (int k = 0; k < 3; ++k) d[k] += s * gw[k];
             } else if (material[j] == MAT_BOUNDARY) {
                 float s = -c->rho0 * volume[j] * p_rho_i;
@@ -516,7 +529,7 @@ void ora_g1_non_pressure(const ora_config *c, int n, const float *x, const float
             float rn = vnorm(r, 2);
             float gw[2];
             cubic_kernel_derivative(c, r, gw);
-            float s = c->g1_visc_c * (c->g1_mass / density[j]) * v_xy / (rn * rn + c->eps_h2);
+            float s = c->g1_visc_c * (c->g1_mass / density[j]) * v_xy / (sq(rn) + c->eps_h2);
             a[0] += s * gw[0];
             a[1] += s * gw[1];
         }
@@ -539,8 +552,8 @@ void ora_g1_pressure_force(const ora_config *c, int n, const float *x, const flo
             float r[2] = {x[2 * (size_t)i] - x[2 * (size_t)j], x[2 * (size_t)i + 1] - x[2 * (size_t)j + 1]};
             float gw[2];
             cubic_kernel_derivative(c, r, gw);
-            float s = c->g1_press_c * (pressure[i] / (density[i] * density[i]) +
-                                       pressure[j] / (density[j] * density[j]));
+            float s = c->g1_press_c * (pressure[i] / sq(density[i]) +
+                                       pressure[j] / sq(density[j]));
             d[0] += s * gw[0];
             d[1] += s * gw[1];
         }

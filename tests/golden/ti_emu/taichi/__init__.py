@@ -295,7 +295,9 @@ def min(a, b):     # noqa: A001
 
 
 def pow(a, b):     # noqa: A001
-    return np.power(_val(a), _val(b))
+    # scalar `**` goes through numpy's scalar-math path = libm powf for float32; np.power (the
+    # ufunc) may dispatch to a vectorised SVML pow with different last-bit rounding
+    return _val(a) ** _val(b)
 
 
 def sqrt(a):
