@@ -185,10 +185,15 @@ def run_gpu(args):
         step = lambda k=1: eng.step(k)
         sim = None
     else:
-        from ti_sph_b200.sharded import ShardedSim
-        sim = ShardedSim(scene, density_mode=args.mode, device=local_rank)
+        from ti_sph_b200.sharded import ShardedSim, TorchDistComm
+        stream = torch.cuda.Stream()
+        torch.cuda.set_stream(stream)
+        sim = ShardedSim(scene, rank, world, comm=TorchDistComm(device=f"cuda:{local_rank}"),
+                         density_mode=args.mode, device=local_rank)
         eng = sim.engine
+        eng.set_stream(stream.cuda_stream)
         n_total = sim.global_particle_num
+        log(f"[bench] rank {rank}: planes [{sim.plane_lo},{sim.plane_hi}) {sim.initial_owned} particles")
         step = lambda k=1: sim.step(k)
 
     def barrier():

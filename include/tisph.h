@@ -108,7 +108,9 @@ typedef enum tisph_param {
     TISPH_P_DENSITY_MODE = 1,
     TISPH_P_VOLUME_MODE = 2,
     TISPH_P_DIAGNOSTICS = 3,  /* 1: also store a_nonpressure / a_pressure every step */
-    TISPH_P_KERNEL_VARIANT = 4 /* implementation selector for A/B benchmarking (0 = default) */
+    TISPH_P_KERNEL_VARIANT = 4, /* implementation selector for A/B benchmarking (0 = default) */
+    TISPH_P_ID_BASE = 5       /* original id given to the next particle added (auto-increments);
+                                 a sharded run sets it so that ids are global */
 } tisph_param;
 
 const char *tisph_last_error(void);
@@ -164,6 +166,27 @@ int tisph_launch_count(tisph_ctx *ctx, int64_t *launches);
  * (as set by the previous call) is non-zero; the call synchronises the stream. */
 int tisph_stage_times(tisph_ctx *ctx, int32_t enable, float *ms_update, float *ms_density,
                       float *ms_force, int32_t *steps);
+
+/* ---- spatial-slab sharding: one context per GPU, one process per GPU --------------------
+ * The reference is single-device; there is no reference interface to cite.  The cell key is
+ * x-major (partice_systemv4.py:98-100), so a rank that owns the x-planes [plane_lo, plane_hi) of
+ * the grid owns one contiguous range of the sorted arrays.  Per step the host side does
+ *     tisph_shard_pack -> exchange counts -> exchange records (NCCL send/recv between the
+ *     message buffers) -> tisph_shard_append -> tisph_step(ctx, 1).
+ * A record is 12 floats: {x,y,z,mass, vx,vy,vz,volume, density,pressure,material,orig_id}.
+ * After tisph_shard_config every per-particle accessor (tisph_particle_num, tisph_download,
+ * tisph_device_ptr, tisph_state_save/restore) covers the OWNED particles only. */
+/* ghost_planes: 1 when a particle's density needs no neighbour data (density_mode 0 with
+ * volume_mode 0), else 2.  message_capacity: records per message buffer. */
+int tisph_shard_config(tisph_ctx *ctx, int32_t plane_lo, int32_t plane_hi, int32_t ghost_planes,
+                       int32_t has_left, int32_t has_right, int32_t message_capacity);
+/* Fill the two send buffers from the owned particles: every particle within ghost_planes of a
+ * slab face, or beyond it (a migrant), goes to that neighbour.  Synchronous; returns counts. */
+int tisph_shard_pack(tisph_ctx *ctx, int32_t *n_left, int32_t *n_right);
+/* Device pointer of a message buffer: 0 send-left, 1 send-right, 2 recv-left, 3 recv-right. */
+int tisph_shard_buffer(tisph_ctx *ctx, int32_t which, void **ptr, int32_t *capacity_records);
+/* Make the received records part of the particle set of the coming step. */
+int tisph_shard_append(tisph_ctx *ctx, int32_t n_from_left, int32_t n_from_right);
 
 #ifdef __cplusplus
 }

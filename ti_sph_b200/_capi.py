@@ -39,7 +39,7 @@ F_X, F_V, F_MASS, F_VOLUME, F_DENSITY, F_PRESSURE, F_MATERIAL, F_COLOR, F_GRID_I
 # enum tisph_stage
 STAGE_UPDATE, STAGE_DENSITY, STAGE_FORCE_ADVECT = range(3)
 # enum tisph_param
-P_DT, P_DENSITY_MODE, P_VOLUME_MODE, P_DIAGNOSTICS, P_KERNEL_VARIANT = range(5)
+P_DT, P_DENSITY_MODE, P_VOLUME_MODE, P_DIAGNOSTICS, P_KERNEL_VARIANT, P_ID_BASE = range(6)
 
 ERR_NO_DEVICE = -5
 
@@ -67,6 +67,10 @@ SYMBOLS = {
     "tisph_sync": (C.c_int, [_vp]),
     "tisph_launch_count": (C.c_int, [_vp, C.POINTER(C.c_int64)]),
     "tisph_stage_times": (C.c_int, [_vp, _i32, _fp, _fp, _fp, _ip]),
+    "tisph_shard_config": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _i32]),
+    "tisph_shard_pack": (C.c_int, [_vp, _ip, _ip]),
+    "tisph_shard_buffer": (C.c_int, [_vp, _i32, C.POINTER(_vp), _ip]),
+    "tisph_shard_append": (C.c_int, [_vp, _i32, _i32]),
 }
 
 

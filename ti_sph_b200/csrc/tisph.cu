@@ -12,6 +12,7 @@
 #include "tisph.h"
 #include "tisph_kernels.cuh"
 #include "tisph_walk.cuh"
+#include "tisph_shard.cuh"
 
 using namespace tisph;
 
@@ -74,6 +75,19 @@ struct tisph_ctx {
     int snap_n = -1;
     int diagnostics = 0;
     int variant = 0;
+    // slab sharding (tisph_shard.cuh)
+    int *rank_key = nullptr;
+    bool sharded = false;
+    int plane_lo = 0, plane_hi = 0, ghost = 1, has_left = 0, has_right = 0;
+    int in_off = 0;                    // first record of the input slice inside P/V/Q[cur]
+    bool appended = false;             // between tisph_shard_append and the step
+    int o_lo = 0, o_hi = 0;            // owned slice of the sorted arrays (host copy)
+    bool range_valid = true;
+    int* range_dev = nullptr;          // {o_lo, o_hi} on the device
+    ShardCounters* shard_ctr = nullptr;
+    float4* msg[4] = {nullptr, nullptr, nullptr, nullptr};   // send_left, send_right, recv_left, recv_right
+    int msg_cap = 0;                   // records per message buffer
+    int id_base = 0;                   // original id of the next particle added
     int64_t launches = 0;
     // stage timing
     int timing = 0, timed = 0;
@@ -111,8 +125,8 @@ static void fill_params(tisph_ctx* c) {
     s.density_mode = g.density_mode; s.volume_mode = g.volume_mode;
     float e = g.exponent;
     s.int_exponent = (e >= 1.0f && e <= 64.0f && e == floorf(e)) ? (int)e : 0;
-    s.owned_lo = 0;
-    s.owned_hi = 0x7fffffff;
+    s.own_key_lo = 0; s.own_key_hi = 0x7fffffff;
+    s.walk_key_lo = 0; s.walk_key_hi = 0x7fffffff;
 }
 
 template <typename T>
@@ -121,6 +135,33 @@ static cudaError_t dalloc(T** p, size_t count) {
 }
 
 static inline int nblocks(int n, int t) { return (n + t - 1) / t; }
+
+// ------------------------------------------------------------------- owned slice (sharding)
+// every particle in [0, n) of the current arrays is owned (fresh / restored state)
+static int set_owned_all(tisph_ctx* c) {
+    c->in_off = 0;
+    c->o_lo = 0;
+    c->o_hi = c->n;
+    c->range_valid = true;
+    if (c->sharded) {
+        int r[2] = {0, c->n};
+        CU(cudaMemcpyAsync(c->range_dev, r, sizeof(r), cudaMemcpyHostToDevice, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+    }
+    return TISPH_OK;
+}
+
+// host copy of the owned slice of the sorted arrays; synchronises only when sharded and stale
+static int ensure_range(tisph_ctx* c) {
+    if (!c->sharded) { c->o_lo = 0; c->o_hi = c->n; return TISPH_OK; }
+    if (c->range_valid) return TISPH_OK;
+    int r[2];
+    CU(cudaMemcpyAsync(r, c->range_dev, sizeof(r), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    c->o_lo = r[0]; c->o_hi = r[1];
+    c->range_valid = true;
+    return TISPH_OK;
+}
 
 // ------------------------------------------------------------------------------- stages
 static int run_update(tisph_ctx* c) {
@@ -132,16 +173,26 @@ static int run_update(tisph_ctx* c) {
     int nb_cells = nblocks(c->ncell, SCAN_TILE);
     CU(cudaMemsetAsync(c->cell_count, 0, sizeof(int) * (size_t)c->ncell, st));
     CU(cudaMemsetAsync(c->ctr, 0, sizeof(StepCounters), st));
-    k_bin<<<nblocks(c->n, 256), 256, 0, st>>>(c->sp, c->P[a], c->keys, c->arrival, c->cell_count, c->err_dev);
+    const float4 *Pin = c->P[a] + c->in_off, *Vin = c->V[a] + c->in_off, *Qin = c->Q[a] + c->in_off;
+    k_bin<<<nblocks(c->n, 256), 256, 0, st>>>(c->sp, Pin, c->keys, c->arrival, c->cell_count, c->err_dev);
     k_scan_reduce<<<nb_cells, SCAN_THREADS, 0, st>>>(c->cell_count, c->ncell, c->block_sums);
     k_scan_spine<<<1, 1024, 0, st>>>(c->block_sums, nb_cells);
     k_scan_apply<<<nb_cells, SCAN_THREADS, 0, st>>>(c->cell_count, c->ncell, c->block_sums, c->cell_end);
-    k_place<<<nblocks(c->n, 256), 256, 0, st>>>(c->n, c->keys, c->arrival, c->cell_end, c->ids);
-    k_reorder<<<nblocks(c->n, 256), 256, 0, st>>>(c->n, c->keys, c->ids, c->cell_end, c->P[a], c->V[a],
-                                                  c->Q[a], c->P[b], c->V[b], c->Q[b], c->keys_sorted);
-    k_items<<<nblocks(c->ncell, 256), 256, 0, st>>>(c->ncell, c->cell_end, c->items, c->ctr);
+    k_place<<<nblocks(c->n, 256), 256, 0, st>>>(c->n, c->keys, c->arrival, c->cell_end, c->ids,
+                                                c->sharded ? Qin : nullptr, c->rank_key);
+    k_reorder<<<nblocks(c->n, 256), 256, 0, st>>>(c->n, c->keys, c->ids, c->rank_key, c->cell_end, Pin, Vin,
+                                                  Qin, c->P[b], c->V[b], c->Q[b], c->keys_sorted);
+    k_items<<<nblocks(c->ncell, 256), 256, 0, st>>>(c->ncell, c->sp.walk_key_lo, c->sp.walk_key_hi, c->cell_end,
+                                                    c->items, c->ctr);
     c->launches += 7;
+    if (c->sharded) {
+        k_owned_range<<<1, 1, 0, st>>>(c->cell_end, c->ncell, c->sp.own_key_lo, c->sp.own_key_hi, c->range_dev);
+        c->launches += 1;
+        c->range_valid = false;
+    }
     CU(cudaGetLastError());
+    c->in_off = 0;
+    c->appended = false;
     c->cur = b;
     c->phase = 1;
     c->have_sorted = true;
@@ -223,6 +274,7 @@ int tisph_create(const tisph_config* cfg, tisph_ctx** out) {
     A(dalloc(&c->D, cap)); A(dalloc(&c->dvel, cap));
     A(dalloc(&c->S, cap)); A(dalloc(&c->ncount, cap));
     A(dalloc(&c->keys, cap)); A(dalloc(&c->arrival, cap)); A(dalloc(&c->ids, cap)); A(dalloc(&c->keys_sorted, cap));
+    A(dalloc(&c->rank_key, cap)); A(dalloc(&c->range_dev, 2)); A(dalloc(&c->shard_ctr, 1));
     A(dalloc(&c->cell_count, (size_t)c->ncell)); A(dalloc(&c->cell_end, (size_t)c->ncell));
     A(dalloc(&c->block_sums, (size_t)nblocks(c->ncell, SCAN_TILE) + 1024));
     A(dalloc(&c->color, cap * 3));
@@ -287,6 +339,8 @@ int tisph_destroy(tisph_ctx* c) {
     cudaFree(c->block_sums); cudaFree(c->color); cudaFree(c->err_dev); cudaFree(c->staging);
     cudaFree(c->items); cudaFree(c->ctr); cudaFree(c->fb_d); cudaFree(c->fb_f); cudaFree(c->item_flags);
     cudaFree(c->Lg); cudaFree(c->Lcnt);
+    cudaFree(c->rank_key); cudaFree(c->range_dev); cudaFree(c->shard_ctr);
+    for (int k = 0; k < 4; ++k) cudaFree(c->msg[k]);
     if (c->ev_made)
         for (int s = 0; s < MAX_TIMED_STEPS; ++s)
             for (int k = 0; k < 4; ++k) cudaEventDestroy(c->ev[s][k]);
@@ -302,6 +356,8 @@ int tisph_add_particles(tisph_ctx* c, int32_t n, const float* pos, const float* 
     if (n < 0 || !pos || !vel || !density || !pressure || !material)
         return fail(TISPH_ERR_INVALID, "null/negative argument");
     if (c->phase != 0) return fail(TISPH_ERR_INVALID, "cannot add particles in the middle of a step");
+    if (c->appended || (c->sharded && c->have_sorted))
+        return fail(TISPH_ERR_INVALID, "a sharded context takes particles only before its first step");
     if ((int64_t)c->n + n > c->cap)
         return fail(TISPH_ERR_CAPACITY, "particle_num %d + %d exceeds particle_max_num %d", c->n, n, c->cap);
     if (n == 0) return TISPH_OK;
@@ -323,7 +379,7 @@ int tisph_add_particles(tisph_ctx* c, int32_t n, const float* pos, const float* 
         CU(cudaMemcpyAsync(d_rho, density + done, (size_t)m * 4, cudaMemcpyHostToDevice, st));
         CU(cudaMemcpyAsync(d_pr, pressure + done, (size_t)m * 4, cudaMemcpyHostToDevice, st));
         CU(cudaMemcpyAsync(d_mat, material + done, (size_t)m * 4, cudaMemcpyHostToDevice, st));
-        k_pack_particles<<<nblocks(m, 256), 256, 0, st>>>(m, dim, c->n + done, c->cfg.m_V0, d_pos, d_vel,
+        k_pack_particles<<<nblocks(m, 256), 256, 0, st>>>(m, dim, c->n + done, c->id_base + done, c->cfg.m_V0, d_pos, d_vel,
                                                           d_rho, d_pr, d_mat, c->P[c->cur], c->V[c->cur],
                                                           c->Q[c->cur]);
         c->launches += 1;
@@ -331,27 +387,37 @@ int tisph_add_particles(tisph_ctx* c, int32_t n, const float* pos, const float* 
         CU(cudaStreamSynchronize(st));   // staging is reused by the next slice
     }
     size_t cc = (size_t)c->color_comp;
-    if (color)
-        CU(cudaMemcpyAsync(c->color + (size_t)c->n * cc, color, (size_t)n * cc * 4, cudaMemcpyHostToDevice, st));
-    else
-        CU(cudaMemsetAsync(c->color + (size_t)c->n * cc, 0, (size_t)n * cc * 4, st));
+    if (!c->sharded) {   // colour is looked up by original id; a shard sees ids beyond its capacity
+        if (color)
+            CU(cudaMemcpyAsync(c->color + (size_t)c->n * cc, color, (size_t)n * cc * 4, cudaMemcpyHostToDevice, st));
+        else
+            CU(cudaMemsetAsync(c->color + (size_t)c->n * cc, 0, (size_t)n * cc * 4, st));
+    }
     CU(cudaStreamSynchronize(st));
     c->n += n;
+    c->id_base += n;
     c->sp.n = c->n;
     c->have_sorted = false;
-    return TISPH_OK;
+    return set_owned_all(c);
 }
 
 int tisph_reset(tisph_ctx* c) {
     CHECK_CTX(c);
     CU(cudaStreamSynchronize(c->stream));
-    c->n = 0; c->sp.n = 0; c->phase = 0; c->have_sorted = false;
+    c->n = 0; c->sp.n = 0; c->phase = 0; c->have_sorted = false; c->id_base = 0;
     CU(cudaMemsetAsync(c->err_dev, 0, 16, c->stream));
-    return TISPH_OK;
+    return set_owned_all(c);
 }
 
 int tisph_particle_num(tisph_ctx* c, int32_t* n) {
     if (!c || !n) return fail(TISPH_ERR_INVALID, "null argument");
+    if (c->sharded) {              // owned particles only (ghosts are not this rank's)
+        CU(cudaSetDevice(c->cfg.device));
+        int rc = ensure_range(c);
+        if (rc) return rc;
+        *n = c->o_hi - c->o_lo;
+        return TISPH_OK;
+    }
     *n = c->n;
     return TISPH_OK;
 }
@@ -361,11 +427,15 @@ int tisph_state_save(tisph_ctx* c) {
     if (c->phase != 0) return fail(TISPH_ERR_INVALID, "cannot save in the middle of a step");
     size_t cap = (size_t)c->cap;
     if (!c->snapP) { CU(dalloc(&c->snapP, cap)); CU(dalloc(&c->snapV, cap)); CU(dalloc(&c->snapQ, cap)); }
-    size_t bytes = (size_t)c->n * sizeof(float4);
-    CU(cudaMemcpyAsync(c->snapP, c->P[c->cur], bytes, cudaMemcpyDeviceToDevice, c->stream));
-    CU(cudaMemcpyAsync(c->snapV, c->V[c->cur], bytes, cudaMemcpyDeviceToDevice, c->stream));
-    CU(cudaMemcpyAsync(c->snapQ, c->Q[c->cur], bytes, cudaMemcpyDeviceToDevice, c->stream));
-    c->snap_n = c->n;
+    if (c->appended) return fail(TISPH_ERR_INVALID, "cannot save between shard_append and the step");
+    int rc = ensure_range(c);
+    if (rc) return rc;
+    int cnt = c->o_hi - c->o_lo;               // owned particles only
+    size_t bytes = (size_t)cnt * sizeof(float4);
+    CU(cudaMemcpyAsync(c->snapP, c->P[c->cur] + c->o_lo, bytes, cudaMemcpyDeviceToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->snapV, c->V[c->cur] + c->o_lo, bytes, cudaMemcpyDeviceToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->snapQ, c->Q[c->cur] + c->o_lo, bytes, cudaMemcpyDeviceToDevice, c->stream));
+    c->snap_n = cnt;
     return TISPH_OK;
 }
 
@@ -380,7 +450,7 @@ int tisph_state_restore(tisph_ctx* c) {
     c->n = c->snap_n;
     c->sp.n = c->n;
     c->have_sorted = false;
-    return TISPH_OK;
+    return set_owned_all(c);
 }
 
 static int make_events(tisph_ctx* c) {
@@ -394,6 +464,8 @@ static int make_events(tisph_ctx* c) {
 int tisph_step(tisph_ctx* c, int32_t nsteps) {
     CHECK_CTX(c);
     if (c->phase != 0) return fail(TISPH_ERR_INVALID, "step issued in the middle of a staged step");
+    if (c->sharded && nsteps > 1)
+        return fail(TISPH_ERR_INVALID, "a sharded context needs a halo exchange before every step");
     for (int s = 0; s < nsteps; ++s) {
         bool t = c->timing && c->timed < MAX_TIMED_STEPS;
         int rc;
@@ -439,7 +511,10 @@ int tisph_download(tisph_ctx* c, int32_t field, void* dst, size_t bytes) {
     CHECK_CTX(c);
     if (!dst) return fail(TISPH_ERR_INVALID, "null destination");
     cudaStream_t st = c->stream;
-    int n = c->n, dim = c->cfg.dim, cur = c->cur;
+    if (c->appended) return fail(TISPH_ERR_INVALID, "cannot download between shard_append and the step");
+    { int rc = ensure_range(c); if (rc) return rc; }
+    const int off = c->o_lo;                    // owned slice (0 unless sharded)
+    int n = c->o_hi - c->o_lo, dim = c->cfg.dim, cur = c->cur;
     const float4* src = nullptr;
     int comp0 = 0, ncomp = 1;
     const void* direct = nullptr;   // already in the reference layout on the device
@@ -464,9 +539,13 @@ int tisph_download(tisph_ctx* c, int32_t field, void* dst, size_t bytes) {
         case TISPH_F_GRID_IDS: direct = c->keys_sorted; break;
         case TISPH_F_GRID_PARTICLES_NUM: direct = c->cell_end; count = (size_t)c->ncell; break;
         case TISPH_F_CELL_COUNT: direct = c->cell_count; count = (size_t)c->ncell; break;
-        case TISPH_F_COLOR: ncomp = c->color_comp; break;
+        case TISPH_F_COLOR:
+            if (c->sharded) return fail(TISPH_ERR_INVALID, "colour is kept by the host side of a sharded run");
+            ncomp = c->color_comp; break;
         default: return fail(TISPH_ERR_INVALID, "unknown field %d", field);
     }
+    if (src) src += off;
+    if (direct && count == (size_t)n) direct = (const char*)direct + (size_t)off * 4;
     size_t need = count * (size_t)ncomp * 4;
     if (bytes != need) return fail(TISPH_ERR_INVALID, "field %d needs %zu bytes, got %zu", field, need, bytes);
     if (need == 0) return TISPH_OK;
@@ -475,7 +554,7 @@ int tisph_download(tisph_ctx* c, int32_t field, void* dst, size_t bytes) {
     } else {
         if (need > c->staging_bytes) return fail(TISPH_ERR_INVALID, "staging buffer too small");
         if (field == TISPH_F_COLOR)
-            k_gather_color<<<nblocks(n, 256), 256, 0, st>>>(n, ncomp, c->Q[cur], c->color, (int*)c->staging);
+            k_gather_color<<<nblocks(n, 256), 256, 0, st>>>(n, ncomp, c->Q[cur] + off, c->color, (int*)c->staging);
         else
             k_unpack<<<nblocks(n, 256), 256, 0, st>>>(n, src, comp0, ncomp, (uint32_t*)c->staging);
         c->launches += 1;
@@ -505,10 +584,12 @@ int tisph_upload_xv(tisph_ctx* c, const float* pos, const float* vel) {
 
 int tisph_device_ptr(tisph_ctx* c, int32_t field, void** ptr, int32_t* stride_bytes) {
     if (!c || !ptr) return fail(TISPH_ERR_INVALID, "null argument");
+    CU(cudaSetDevice(c->cfg.device));
+    { int rc = ensure_range(c); if (rc) return rc; }
     switch (field) {
-        case TISPH_F_X: *ptr = c->P[c->cur]; break;
-        case TISPH_F_V: *ptr = c->V[c->cur]; break;
-        case TISPH_F_D_VELOCITY: *ptr = c->dvel; break;
+        case TISPH_F_X: *ptr = c->P[c->cur] + c->o_lo; break;
+        case TISPH_F_V: *ptr = c->V[c->cur] + c->o_lo; break;
+        case TISPH_F_D_VELOCITY: *ptr = c->dvel + c->o_lo; break;
         default: return fail(TISPH_ERR_INVALID, "field %d has no zero-copy view", field);
     }
     if (stride_bytes) *stride_bytes = 16;
@@ -531,6 +612,7 @@ int tisph_set_param(tisph_ctx* c, int32_t param, double value) {
             }
             return TISPH_OK;
         case TISPH_P_KERNEL_VARIANT: c->variant = (int)value; return TISPH_OK;
+        case TISPH_P_ID_BASE: c->id_base = (int)value; return TISPH_OK;
     }
     return fail(TISPH_ERR_INVALID, "unknown parameter %d", param);
 }
@@ -543,6 +625,7 @@ int tisph_get_param(tisph_ctx* c, int32_t param, double* value) {
         case TISPH_P_VOLUME_MODE: *value = c->cfg.volume_mode; return TISPH_OK;
         case TISPH_P_DIAGNOSTICS: *value = c->diagnostics; return TISPH_OK;
         case TISPH_P_KERNEL_VARIANT: *value = c->variant; return TISPH_OK;
+        case TISPH_P_ID_BASE: *value = c->id_base; return TISPH_OK;
     }
     return fail(TISPH_ERR_INVALID, "unknown parameter %d", param);
 }
@@ -579,6 +662,100 @@ int tisph_stage_times(tisph_ctx* c, int32_t enable, float* ms_update, float* ms_
     c->timed = 0;
     c->timing = enable != 0;
     if (c->timing) return make_events(c);
+    return TISPH_OK;
+}
+
+// ------------------------------------------------------------------ slab sharding (8(e))
+int tisph_shard_config(tisph_ctx* c, int32_t plane_lo, int32_t plane_hi, int32_t ghost_planes,
+                       int32_t has_left, int32_t has_right, int32_t message_capacity) {
+    CHECK_CTX(c);
+    if (c->have_sorted || c->appended) return fail(TISPH_ERR_INVALID, "configure the slab before the first step");
+    if (plane_lo < 0 || plane_hi > c->sp.gx || plane_lo >= plane_hi || ghost_planes < 1 || ghost_planes > 2 ||
+        message_capacity <= 0)
+        return fail(TISPH_ERR_INVALID, "bad slab [%d,%d) / ghost %d / capacity %d", plane_lo, plane_hi,
+                    ghost_planes, message_capacity);
+    c->sharded = true;
+    c->plane_lo = plane_lo; c->plane_hi = plane_hi; c->ghost = ghost_planes;
+    c->has_left = has_left != 0; c->has_right = has_right != 0;
+    const int plane = c->sp.gy * c->sp.gz;
+    c->sp.own_key_lo = plane_lo * plane;
+    c->sp.own_key_hi = plane_hi * plane;
+    c->sp.walk_key_lo = (plane_lo - 1 > 0 ? plane_lo - 1 : 0) * plane;
+    c->sp.walk_key_hi = (plane_hi + 1 < c->sp.gx ? plane_hi + 1 : c->sp.gx) * plane;
+    if (message_capacity != c->msg_cap) {
+        for (int k = 0; k < 4; ++k) { cudaFree(c->msg[k]); c->msg[k] = nullptr; }
+        for (int k = 0; k < 4; ++k) CU(dalloc(&c->msg[k], (size_t)message_capacity * SHARD_REC_F4));
+        c->msg_cap = message_capacity;
+    }
+    return set_owned_all(c);
+}
+
+int tisph_shard_pack(tisph_ctx* c, int32_t* n_left, int32_t* n_right) {
+    CHECK_CTX(c);
+    if (!c->sharded) return fail(TISPH_ERR_INVALID, "tisph_shard_config has not been called");
+    if (c->phase != 0 || c->appended) return fail(TISPH_ERR_INVALID, "pack issued out of order");
+    if (!n_left || !n_right) return fail(TISPH_ERR_INVALID, "null argument");
+    cudaStream_t st = c->stream;
+    CU(cudaMemsetAsync(c->shard_ctr, 0, sizeof(ShardCounters), st));
+    // the owned slice is read from device memory: no host round trip between the step and the pack
+    const int n_upper = c->range_valid ? c->o_hi - c->o_lo : c->n;
+    if (n_upper > 0) {
+        k_shard_pack<<<nblocks(n_upper, 256), 256, 0, st>>>(
+            c->sp, n_upper, c->range_dev, c->plane_lo, c->plane_hi, c->ghost, c->has_left, c->has_right,
+            c->msg_cap, c->P[c->cur], c->V[c->cur], c->Q[c->cur], c->msg[0], c->msg[1], c->shard_ctr);
+        c->launches += 1;
+        CU(cudaGetLastError());
+    }
+    struct { ShardCounters k; } h;
+    int r[2];
+    CU(cudaMemcpyAsync(&h.k, c->shard_ctr, sizeof(ShardCounters), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(r, c->range_dev, sizeof(r), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    c->o_lo = r[0]; c->o_hi = r[1]; c->range_valid = true;
+    if (h.k.overflow)
+        return fail(TISPH_ERR_CAPACITY, "halo message buffers too small: %d record(s) dropped (capacity %d)",
+                    h.k.overflow, c->msg_cap);
+    if (h.k.lost)
+        return fail(TISPH_ERR_DOMAIN, "%d particle(s) crossed more than %d cell plane(s) beyond the slab in one step",
+                    h.k.lost, c->ghost);
+    *n_left = h.k.n_left;
+    *n_right = h.k.n_right;
+    return TISPH_OK;
+}
+
+int tisph_shard_buffer(tisph_ctx* c, int32_t which, void** ptr, int32_t* capacity_records) {
+    if (!c || !ptr) return fail(TISPH_ERR_INVALID, "null argument");
+    if (!c->sharded || which < 0 || which > 3) return fail(TISPH_ERR_INVALID, "no such message buffer");
+    *ptr = c->msg[which];
+    if (capacity_records) *capacity_records = c->msg_cap;
+    return TISPH_OK;
+}
+
+int tisph_shard_append(tisph_ctx* c, int32_t n_from_left, int32_t n_from_right) {
+    CHECK_CTX(c);
+    if (!c->sharded) return fail(TISPH_ERR_INVALID, "tisph_shard_config has not been called");
+    if (c->phase != 0 || c->appended || !c->range_valid) return fail(TISPH_ERR_INVALID, "append issued out of order");
+    if (n_from_left < 0 || n_from_right < 0 || n_from_left > c->msg_cap || n_from_right > c->msg_cap)
+        return fail(TISPH_ERR_INVALID, "bad record counts %d / %d", n_from_left, n_from_right);
+    int64_t end = (int64_t)c->o_hi + n_from_left + n_from_right;
+    if (end > c->cap)
+        return fail(TISPH_ERR_CAPACITY, "owned slice [%d,%d) + %d + %d halo records exceed the capacity %d",
+                    c->o_lo, c->o_hi, n_from_left, n_from_right, c->cap);
+    cudaStream_t st = c->stream;
+    int cur = c->cur;
+    if (n_from_left > 0)
+        k_shard_append<<<nblocks(n_from_left, 256), 256, 0, st>>>(n_from_left, c->msg[2], c->o_hi, c->P[cur],
+                                                                  c->V[cur], c->Q[cur]);
+    if (n_from_right > 0)
+        k_shard_append<<<nblocks(n_from_right, 256), 256, 0, st>>>(n_from_right, c->msg[3], c->o_hi + n_from_left,
+                                                                   c->P[cur], c->V[cur], c->Q[cur]);
+    c->launches += (n_from_left > 0) + (n_from_right > 0);
+    CU(cudaGetLastError());
+    c->in_off = c->o_lo;
+    c->n = (c->o_hi - c->o_lo) + n_from_left + n_from_right;
+    c->sp.n = c->n;
+    c->appended = true;
+    c->have_sorted = false;
     return TISPH_OK;
 }
 

@@ -29,7 +29,9 @@ struct SimParams {
     float g1_visc_c, g1_mass, g1_press_c, m_V0;
     int density_mode, volume_mode;
     int int_exponent;      // exponent if it is a small positive integer, else 0
-    int owned_lo, owned_hi;   // sorted-index range that is advanced (ghosts lie outside)
+    // slab sharding (tisph_shard.cuh): cell-key ranges [lo, hi).  Unsharded: [0, INT_MAX).
+    int own_key_lo, own_key_hi;     // cells whose particles this rank advances
+    int walk_key_lo, walk_key_hi;   // cells that get work items (own planes + one ghost plane each side)
 };
 
 // cell = (int)(x / grid_size): IEEE f32 division then truncation (partice_systemv4.py:86-92)

@@ -160,18 +160,24 @@ __device__ __forceinline__ int cell_start(const int* __restrict__ cell_end, int 
     return c > 0 ? cell_end[c - 1] : 0;
 }
 
+// `rank_key` is what the canonical intra-cell order sorts by: the index in the unsorted array
+// (the reference's serial order) or, when Qin is given (sharded runs, where array positions are
+// rank-local), the global original id of the particle.
 __global__ void __launch_bounds__(256)
 k_place(int n, const int* __restrict__ keys, const int* __restrict__ arrival,
-        const int* __restrict__ cell_end, int* __restrict__ ids) {
+        const int* __restrict__ cell_end, int* __restrict__ ids, const float4* __restrict__ Qin,
+        int* __restrict__ rank_key) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     int key = keys[i];
-    ids[cell_start(cell_end, key) + arrival[i]] = i;
+    int slot = cell_start(cell_end, key) + arrival[i];
+    ids[slot] = i;
+    rank_key[slot] = Qin ? __float_as_int(Qin[i].w) : i;
 }
 
 __global__ void __launch_bounds__(256)
 k_reorder(int n, const int* __restrict__ keys, const int* __restrict__ ids,
-          const int* __restrict__ cell_end, const float4* __restrict__ Pin,
+          const int* __restrict__ rank_key, const int* __restrict__ cell_end, const float4* __restrict__ Pin,
           const float4* __restrict__ Vin, const float4* __restrict__ Qin,
           float4* __restrict__ Pout, float4* __restrict__ Vout, float4* __restrict__ Qout,
           int* __restrict__ keys_sorted) {
@@ -181,7 +187,8 @@ k_reorder(int n, const int* __restrict__ keys, const int* __restrict__ ids,
     int key = keys[id];
     int b = cell_start(cell_end, key), e = cell_end[key];
     int cnt = 0;
-    for (int t = b; t < e; ++t) cnt += (ids[t] < id) ? 1 : 0;
+    const int mine = rank_key[s];
+    for (int t = b; t < e; ++t) cnt += (rank_key[t] < mine) ? 1 : 0;
     int dst = b + cnt;
     Pout[dst] = Pin[id];
     Vout[dst] = Vin[id];
@@ -250,7 +257,7 @@ __device__ __forceinline__ int tile_to_global(const CellRanges& R, int e) {
 // Host<->device layout conversion (add_particles :171-204, dump/copy_to_numpy :279-307)
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-k_pack_particles(int n, int dim, int first, float m_V0, const float* __restrict__ pos,
+k_pack_particles(int n, int dim, int first, int id_first, float m_V0, const float* __restrict__ pos,
                  const float* __restrict__ vel, const float* __restrict__ density,
                  const float* __restrict__ pressure, const int* __restrict__ material,
                  float4* __restrict__ P, float4* __restrict__ V, float4* __restrict__ Q) {
@@ -264,7 +271,7 @@ k_pack_particles(int n, int dim, int first, float m_V0, const float* __restrict_
     P[first + i] = make_float4(x, y, z, mass);
     V[first + i] = make_float4(vx, vy, vz, volume);
     Q[first + i] = make_float4(rho, pressure[i], __int_as_float(material[i]),
-                               __int_as_float(first + i));
+                               __int_as_float(id_first + i));
 }
 
 __global__ void __launch_bounds__(256)

@@ -44,11 +44,11 @@ struct StepCounters {
 
 // item = {cell, first target of the pass relative to the cell's first particle}
 __global__ void __launch_bounds__(256)
-k_items(int ncell, const int* __restrict__ cell_end, int2* __restrict__ items,
+k_items(int ncell, int key_lo, int key_hi, const int* __restrict__ cell_end, int2* __restrict__ items,
         StepCounters* __restrict__ ctr) {
     int c = blockIdx.x * blockDim.x + threadIdx.x;
     int cnt = 0;
-    if (c < ncell) cnt = cell_end[c] - cell_start(cell_end, c);
+    if (c < ncell && c >= key_lo && c < key_hi) cnt = cell_end[c] - cell_start(cell_end, c);
     int ni = cnt == 0 ? 0 : (cnt + 63) >> 6;
     // warp-aggregated reservation keeps the list roughly in cell order (L2 locality of the walks)
     int lane = threadIdx.x & 31;
@@ -228,7 +228,8 @@ k_density_list(SimParams sp, const int* __restrict__ cell_end, const int2* __res
             }
             continue;
         }
-        const bool keep_list = it < list_items_cap;
+        const bool own = G.c >= sp.own_key_lo && G.c < sp.own_key_hi;   // ghost cells get no force walk
+        const bool keep_list = own && it < list_items_cap;
         if (tid == 0) s_over = keep_list ? 0 : 1;
         // ---- stage the tile ---------------------------------------------------------------
         const int nchunk = (G.total + CHUNK - 1) / CHUNK;
@@ -308,7 +309,7 @@ k_density_list(SimParams sp, const int* __restrict__ cell_end, const int2* __res
         __syncthreads();
         if (tid == 0) {
             flags[it] = (unsigned char)s_over;
-            if (s_over) fb_f[atomicAdd(&ctr->n_fb_f, 1)] = it;
+            if (s_over && own) fb_f[atomicAdd(&ctr->n_fb_f, 1)] = it;
         }
         if (split == 0 && active) {
             for (int s = 1; s < G.nsplit; ++s) {
@@ -368,6 +369,7 @@ k_force_list(SimParams sp, const int* __restrict__ cell_end, const int2* __restr
         const int it = next_item(&ctr->work_f, &s_slot);
         if (it >= ctr->n_items) break;
         if (flags[it]) continue;                         // handled by k_force_fb
+        if (items[it].x < sp.own_key_lo || items[it].x >= sp.own_key_hi) continue;   // ghost cell: not advanced here
         ItemGeom G;
         item_setup(sp, cell_end, items[it], R, G);
         stage_force_tile(R, 0, G.total, G.total, Pin, Vin, Qin, D, tP, tV, tR);
@@ -378,7 +380,7 @@ k_force_list(SimParams sp, const int* __restrict__ cell_end, const int2* __restr
         const float4 vi = active ? Vin[i] : make_float4(0.f, 0.f, 0.f, 0.f);
         const float4 di = active ? D[i] : make_float4(1.f, 0.f, 1.f, 0.f);
         const float4 qi = active ? Qin[i] : make_float4(0.f, 0.f, 0.f, 0.f);
-        const bool walker = active && __float_as_int(qi.z) == MAT_FLUID && i >= sp.owned_lo && i < sp.owned_hi;
+        const bool walker = active && __float_as_int(qi.z) == MAT_FLUID;
         const int self_lo = R.gb[4], self_len = R.off[5] - R.off[4];
         const int self_t = (active && i >= self_lo && i < self_lo + self_len) ? R.off[4] + (i - self_lo) : -1;
         const float coh_i = 0.01f / pi.w;                         // wcsphv2.py:64
@@ -536,6 +538,7 @@ k_force_fb(SimParams sp, const int* __restrict__ cell_end, const int2* __restric
         const int wk = next_item(&ctr->work_fb_f, &s_slot);
         if (wk >= ctr->n_fb_f) break;
         const int it = fb_f[wk];
+        if (items[it].x < sp.own_key_lo || items[it].x >= sp.own_key_hi) continue;   // ghost cell
         ItemGeom G;
         item_setup(sp, cell_end, items[it], R, G);
         const int t_local = tid % G.tl, split = tid / G.tl;
@@ -545,7 +548,7 @@ k_force_fb(SimParams sp, const int* __restrict__ cell_end, const int2* __restric
         const float4 vi = active ? Vin[i] : make_float4(0.f, 0.f, 0.f, 0.f);
         const float4 di = active ? D[i] : make_float4(1.f, 0.f, 1.f, 0.f);
         const float4 qi = active ? Qin[i] : make_float4(0.f, 0.f, 0.f, 0.f);
-        const bool walker = active && __float_as_int(qi.z) == MAT_FLUID && i >= sp.owned_lo && i < sp.owned_hi;
+        const bool walker = active && __float_as_int(qi.z) == MAT_FLUID;
         const float xi = walker ? pi.x : -FAR, yi = walker ? pi.y : -FAR, zi = walker ? pi.z : -FAR;
         const int self_lo = R.gb[4], self_len = R.off[5] - R.off[4];
         const int self_e = (active && i >= self_lo && i < self_lo + self_len) ? R.off[4] + (i - self_lo) : -1;

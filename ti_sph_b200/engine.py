@@ -138,3 +138,37 @@ class Engine:
         check(self._lib.tisph_stage_times(self._ctx, int(bool(enable)), C.byref(a), C.byref(b),
                                           C.byref(c), C.byref(s)))
         return {"update_ms": a.value, "density_ms": b.value, "force_ms": c.value, "steps": s.value}
+
+    # -- slab sharding (include/tisph.h, "spatial-slab sharding") ------------------------------
+    def shard_config(self, plane_lo, plane_hi, ghost_planes, has_left, has_right, message_capacity):
+        check(self._lib.tisph_shard_config(self._ctx, int(plane_lo), int(plane_hi), int(ghost_planes),
+                                           int(bool(has_left)), int(bool(has_right)), int(message_capacity)))
+        self._msg_cap = int(message_capacity)
+
+    def shard_pack(self):
+        nl, nr = C.c_int32(), C.c_int32()
+        check(self._lib.tisph_shard_pack(self._ctx, C.byref(nl), C.byref(nr)))
+        return nl.value, nr.value
+
+    def message_tensor(self, which, n):
+        """torch view (no copy) of the first n records of a message buffer:
+        0 send-left, 1 send-right, 2 recv-left, 3 recv-right; a record is 12 f32."""
+        import torch
+        p, cap = C.c_void_p(), C.c_int32()
+        check(self._lib.tisph_shard_buffer(self._ctx, int(which), C.byref(p), C.byref(cap)))
+        if n > cap.value:
+            raise _capi.TisphError(-3, f"{n} halo records exceed the message capacity {cap.value}")
+        if n == 0:
+            return torch.empty((0, 12), dtype=torch.float32, device=f"cuda:{self.config.device}")
+        return torch.as_tensor(_DeviceArray(p.value, (int(n), 12)), device=f"cuda:{self.config.device}")
+
+    def shard_append(self, n_from_left, n_from_right):
+        check(self._lib.tisph_shard_append(self._ctx, int(n_from_left), int(n_from_right)))
+
+
+class _DeviceArray:
+    """__cuda_array_interface__ carrier for a raw device pointer (f32, C-contiguous)."""
+
+    def __init__(self, ptr, shape):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<f4", "data": (int(ptr), False),
+                                         "version": 3, "strides": None}

@@ -1,0 +1,311 @@
+"""Slab-sharded WCSPH step: one process (and one Engine) per GPU, x-slabs, halo exchange + migration.
+
+The reference is single-device; this is the multi-GPU row of SURVEY.md 8(e).
+The cell key is x-major (partice_systemv4.py:98-100), so a rank that owns the x-planes
+[plane_lo, plane_hi) of the grid owns one contiguous range of the sorted particle arrays, and its
+ghost planes are contiguous too: a halo message is a plain run of 48-byte records, packed by one
+kernel (csrc/tisph_shard.cuh) and sent with NCCL send/recv over NVLink -- there is no all-reduce
+or any other collective on the data path.  Per step and rank:
+
+    pack  (owned particles within `ghost` planes of a face, or beyond it = migrants)
+    -> exchange counts with both neighbours -> exchange records
+    -> append -> bin/scan/sort everything -> density on [lo-1, hi] -> forces/advect on [lo, hi)
+
+`ghost` is 1 when a particle's density needs no neighbour data (density_mode "reference" with
+volume_mode "reference": rho = mass W(0), wcsphv2.py:32-34), else 2 -- the densities of the first
+ghost plane are then recomputed locally instead of being exchanged a second time.
+
+Slab edges are chosen once from the per-x-plane particle histogram so that every rank starts
+with the same number of particles (`plan_slabs`).  Intra-cell order is by original particle id
+(the single-GPU engine orders by array position like the serial reference; array positions are
+rank-local here).  Concatenating the ranks' owned particles in rank order gives the global
+cell-sorted order that ParticleSystemV4.dump() of a single engine returns.
+"""
+from functools import reduce
+
+import numpy as np
+
+from . import _capi as K
+from . import scene as sc
+
+LEFT, RIGHT = 0, 1
+SEND_LEFT, SEND_RIGHT, RECV_LEFT, RECV_RIGHT = 0, 1, 2, 3
+FLUID_COLOR = 0x111111            # partice_systemv4.py:144
+
+
+# ------------------------------------------------------------------------------ slab planning
+def x_plane(x, h):
+    """cell plane of x-coordinates: IEEE f32 division, truncation (partice_systemv4.py:86-92)."""
+    return (np.asarray(x, np.float32) / np.float32(h)).astype(np.int32)
+
+
+def plan_slabs(plane_counts, world, min_planes=3):
+    """Edges e[0]=0 < e[1] < ... < e[world]=len(plane_counts): slab k owns planes [e[k], e[k+1]).
+    Cuts are put where the cumulative particle count crosses k/world of the total; every slab is
+    at least `min_planes` thick (the ghost-layer argument of the module docstring needs 3)."""
+    counts = np.asarray(plane_counts, np.int64)
+    gx = len(counts)
+    if world * min_planes > gx:
+        raise ValueError(f"{gx} cell planes cannot be split into {world} slabs of >= {min_planes} planes")
+    cum = np.concatenate([[0], np.cumsum(counts)])
+    total = cum[-1]
+    edges = [0]
+    for k in range(1, world):
+        target = total * k / world
+        e = int(np.searchsorted(cum, target, side="left"))
+        # the cut that leaves the cumulative count closest to the target
+        if e > 0 and abs(cum[e - 1] - target) <= abs(cum[min(e, gx)] - target):
+            e -= 1
+        e = max(e, edges[-1] + min_planes)
+        e = min(e, gx - (world - k) * min_planes)
+        edges.append(e)
+    edges.append(gx)
+    return edges
+
+
+class SceneParts:
+    """The scene's particles in the reference's insertion order (rigid bodies first, then the fluid
+    blocks: partice_systemv4.py:102-146) without materialising them: per-plane histogram and
+    per-slab generation."""
+
+    def __init__(self, scene, rigid_points=()):
+        cfg = scene["configuration"]
+        self.cfg = cfg
+        self.dim = cfg["dim"]
+        assert self.dim == 3
+        self.r = cfg["particleRadius"]
+        self.h = 4.0 * self.r
+        size = np.array(cfg["domainEnd"]) - np.array(cfg["domainStart"])
+        self.grid_num = np.ceil(size / self.h).astype(np.int32)
+        self.parts = []          # (kind, id0, data)
+        nid = 0
+        for body, pts in zip(scene["rigidBodies"], rigid_points):
+            pts = np.asarray(pts, np.float32)
+            order = np.argsort(x_plane(pts[:, 0], self.h), kind="stable")   # ids follow x-planes
+            self.parts.append(("rigid", nid, (pts[order], body)))
+            nid += len(pts)
+        for blk in scene["fluidBlocks"]:
+            start, end = blk["start"], blk["end"]
+            axes = [np.arange(start[i], start[i] + (end[i] - start[i]), self.r) for i in range(3)]
+            pre = sc.cube_particle_num(start, end, self.r, 3)
+            n = reduce(lambda a, b: a * b, [len(a) for a in axes])
+            if pre != n:
+                raise RuntimeError("particle count pre-pass != add_cube count (reference quirk Q10)")
+            self.parts.append(("fluid", nid, (axes, blk)))
+            nid += n
+        self.total = nid
+
+    def plane_counts(self):
+        counts = np.zeros(int(self.grid_num[0]), np.int64)
+        for kind, _, data in self.parts:
+            if kind == "rigid":
+                np.add.at(counts, x_plane(data[0][:, 0], self.h), 1)
+            else:
+                axes, _ = data
+                np.add.at(counts, x_plane(axes[0].astype(np.float32), self.h), len(axes[1]) * len(axes[2]))
+        return counts
+
+    def slab_particles(self, lo, hi):
+        """[(id0, pos, vel, density, material)] of the particles whose x-plane is in [lo, hi);
+        every chunk has contiguous original ids starting at id0."""
+        out = []
+        for kind, id0, data in self.parts:
+            if kind == "rigid":
+                pts, body = data
+                pl = x_plane(pts[:, 0], self.h)
+                a, b = int(np.searchsorted(pl, lo, "left")), int(np.searchsorted(pl, hi, "left"))
+                if b > a:
+                    dens = body.get("density")
+                    out.append((id0 + a, pts[a:b], np.tile(np.array(body["velocity"], np.float32), (b - a, 1)),
+                                np.full(b - a, dens if dens is not None else 1000.0, np.float32),
+                                np.zeros(b - a, np.int32)))
+            else:
+                axes, blk = data
+                pl = x_plane(axes[0].astype(np.float32), self.h)       # non-decreasing in x
+                a, b = int(np.searchsorted(pl, lo, "left")), int(np.searchsorted(pl, hi, "left"))
+                if b > a:
+                    per_layer = len(axes[1]) * len(axes[2])
+                    pos = np.array(np.meshgrid(axes[0][a:b], axes[1], axes[2], indexing="ij"), dtype=np.float32)
+                    pos = np.ascontiguousarray(pos.reshape(3, -1).T)
+                    dens = blk["density"]
+                    out.append((id0 + a * per_layer, pos,
+                                np.full(pos.shape, blk["velocity"], dtype=np.float32),
+                                np.full(len(pos), dens if dens is not None else 1000.0, np.float32),
+                                np.ones(len(pos), np.int32)))
+        return out
+
+    def color_of(self, ids):
+        """ps.color of the particles with these original ids (fluid: 0x111111 in every lane, :144)."""
+        ids = np.asarray(ids)
+        col = np.zeros((len(ids), 3), np.int32)
+        for kind, id0, data in self.parts:
+            n = len(data[0][0]) if kind == "rigid" else reduce(lambda a, b: a * b, [len(a) for a in data[0]])
+            m = (ids >= id0) & (ids < id0 + n)
+            if kind == "fluid":
+                col[m] = FLUID_COLOR
+            else:
+                col[m] = np.array(data[1].get("color", [0, 0, 0]), np.int32)
+        return col
+
+
+# ------------------------------------------------------------------------------ communication
+class TorchDistComm:
+    """Neighbour exchange over torch.distributed (NCCL on GPUs, gloo in the CPU tests)."""
+
+    def __init__(self, group=None, device=None):
+        import torch.distributed as dist
+        self.dist = dist
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        self.device = device
+
+    def exchange(self, rank, send_left, send_right, recv_left, recv_right):
+        """send_* / recv_* are tensors or None; posts everything at once and waits."""
+        dist = self.dist
+        ops = []
+        if recv_left is not None:
+            ops.append(dist.P2POp(dist.irecv, recv_left, rank - 1, self.group))
+        if recv_right is not None:
+            ops.append(dist.P2POp(dist.irecv, recv_right, rank + 1, self.group))
+        if send_left is not None:
+            ops.append(dist.P2POp(dist.isend, send_left, rank - 1, self.group))
+        if send_right is not None:
+            ops.append(dist.P2POp(dist.isend, send_right, rank + 1, self.group))
+        if ops:
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+
+    def all_gather_objects(self, obj):
+        out = [None] * self.world
+        self.dist.all_gather_object(out, obj, group=self.group)
+        return out
+
+
+# ------------------------------------------------------------------------------ one rank
+class ShardedSim:
+    """One rank's slab of a gen-2 (ParticleSystemV4 + WCSPHV2) simulation."""
+
+    def __init__(self, scene, rank, world, comm=None, density_mode="reference", volume_mode="reference",
+                 device=0, rigid_points=(), engine_factory=None, capacity_factor=1.6, edges=None,
+                 message_capacity=None):
+        import torch
+        self.torch = torch
+        self.rank, self.world, self.comm = rank, world, comm
+        self.scene = scene
+        self.parts = SceneParts(scene, rigid_points)
+        self.ghost = 1 if (density_mode == "reference" and volume_mode == "reference") else 2
+        counts = self.parts.plane_counts()
+        self.edges = list(edges) if edges is not None else plan_slabs(counts, world)
+        self.plane_lo, self.plane_hi = self.edges[rank], self.edges[rank + 1]
+        self.has_left, self.has_right = rank > 0, rank < world - 1
+        chunks = self.parts.slab_particles(self.plane_lo, self.plane_hi)
+        n_own = sum(len(c[1]) for c in chunks)
+        halo = int(counts[max(self.plane_lo - self.ghost, 0):self.plane_lo].sum() +
+                   counts[self.plane_hi:self.plane_hi + self.ghost].sum())
+        peak_plane = int(counts.max())
+        if message_capacity is None:
+            message_capacity = max(1024, 2 * (self.ghost + 1) * peak_plane)
+        capacity = int(capacity_factor * (n_own + halo)) + 2 * message_capacity + 1024
+        cfg = sc.gen2_config(scene["configuration"], capacity, device=device,
+                             density_mode={"reference": 0, "summed": 1}[density_mode],
+                             volume_mode={"reference": 0, "akinci": 1}[volume_mode])
+        if engine_factory is None:
+            from .engine import Engine
+            engine_factory = Engine
+        self.engine = eng = engine_factory(cfg)
+        eng.shard_config(self.plane_lo, self.plane_hi, self.ghost, self.has_left, self.has_right,
+                         message_capacity)
+        for id0, pos, vel, dens, mat in chunks:
+            eng.set_param(K.P_ID_BASE, id0)
+            eng.add_particles(pos, vel, dens, np.zeros(len(pos), np.float32), mat)
+        self.global_particle_num = self.parts.total
+        self.initial_owned = n_own
+        self._counts_dev = None
+
+    # -- the phases of one step (LocalCluster drives them for several ranks in one process) -----
+    def pack(self):
+        self._nsend = self.engine.shard_pack()
+        return self._nsend
+
+    def exchange(self):
+        """counts, then records, with both neighbours (torch.distributed)."""
+        torch, eng, comm = self.torch, self.engine, self.comm
+        nl, nr = self._nsend
+        dev = comm.device
+        sc_l = torch.tensor([nl], dtype=torch.int32, device=dev) if self.has_left else None
+        sc_r = torch.tensor([nr], dtype=torch.int32, device=dev) if self.has_right else None
+        rc_l = torch.zeros(1, dtype=torch.int32, device=dev) if self.has_left else None
+        rc_r = torch.zeros(1, dtype=torch.int32, device=dev) if self.has_right else None
+        comm.exchange(self.rank, sc_l, sc_r, rc_l, rc_r)
+        ml = int(rc_l.item()) if self.has_left else 0
+        mr = int(rc_r.item()) if self.has_right else 0
+        comm.exchange(self.rank,
+                      eng.message_tensor(SEND_LEFT, nl) if self.has_left and nl else None,
+                      eng.message_tensor(SEND_RIGHT, nr) if self.has_right and nr else None,
+                      eng.message_tensor(RECV_LEFT, ml) if ml else None,
+                      eng.message_tensor(RECV_RIGHT, mr) if mr else None)
+        self._nrecv = (ml, mr)
+        return self._nrecv
+
+    def compute(self):
+        self.engine.shard_append(*self._nrecv)
+        self.engine.step(1)
+
+    def step(self, nsteps=1):
+        for _ in range(nsteps):
+            self.pack()
+            self.exchange()
+            self.compute()
+
+    # -- state -------------------------------------------------------------------------------
+    def save_state(self):
+        self.engine.save_state()
+
+    def restore_state(self):
+        self.engine.restore_state()
+
+    def dump_local(self):
+        """this rank's owned particles, in sorted order (keys of dump() + 'orig_id')"""
+        e = self.engine
+        ids = e.download(K.F_ORIG_ID)
+        return {"position": e.download(K.F_X), "velocity": e.download(K.F_V),
+                "material": e.download(K.F_MATERIAL), "color": self.parts.color_of(ids), "orig_id": ids}
+
+    def dump(self):
+        """ParticleSystemV4.dump() of the whole simulation on every rank: the ranks' owned
+        particles concatenated in rank order (= global cell-sorted order)."""
+        parts = self.comm.all_gather_objects(self.dump_local())
+        return {k: np.concatenate([p[k] for p in parts]) for k in parts[0]}
+
+
+# ------------------------------------------------------------------------------ in-process cluster
+class LocalCluster:
+    """All ranks of a sharded run inside one process (engines may share one GPU).  Used by the
+    single-GPU parity tests of the shard kernels; messages are device-to-device copies."""
+
+    def __init__(self, scene, world, **kw):
+        self.world = world
+        self.sims = [ShardedSim(scene, r, world, comm=None, **kw) for r in range(world)]
+
+    def step(self, nsteps=1):
+        sims = self.sims
+        for _ in range(nsteps):
+            counts = [s.pack() for s in sims]             # pack synchronises each engine's stream
+            for r, s in enumerate(sims):
+                ml = counts[r - 1][1] if r > 0 else 0
+                mr = counts[r + 1][0] if r < self.world - 1 else 0
+                if ml:
+                    s.engine.message_tensor(RECV_LEFT, ml).copy_(sims[r - 1].engine.message_tensor(SEND_RIGHT, ml))
+                if mr:
+                    s.engine.message_tensor(RECV_RIGHT, mr).copy_(sims[r + 1].engine.message_tensor(SEND_LEFT, mr))
+                s._nrecv = (ml, mr)
+            sync = getattr(sims[0].torch.cuda, "synchronize", None)
+            if sims[0].torch.cuda.is_available():
+                sync()
+            for s in sims:
+                s.compute()
+
+    def dump(self):
+        parts = [s.dump_local() for s in self.sims]
+        return {k: np.concatenate([p[k] for p in parts]) for k in parts[0]}
