@@ -50,8 +50,11 @@ def run_stages(ora, eng, density_mode, p_rtol=RTOL, np_floor=None):
     fl = t["material"] == 1
     dv = np.linalg.norm(eng.download(K.F_V).astype(np.float64) - t["v"], axis=1)
     vscale = np.maximum(np.linalg.norm(t["v"], axis=1), 1.0)
-    assert np.max(dv / vscale) < RTOL + 5 * RTOL * 2e-4 * pfloor
-    assert rel_err(eng.download(K.F_X), t["x"], floor=0.04) < RTOL
+    vtol = RTOL + 5 * RTOL * 2e-4 * pfloor
+    assert np.max(dv / vscale) < vtol
+    # x' = x + dt v' (then the wall clamp): the position inherits dt times the velocity tolerance
+    dx = np.linalg.norm(eng.download(K.F_X).astype(np.float64) - t["x"], axis=1)
+    assert np.all(dx <= RTOL * np.maximum(np.linalg.norm(t["x"], axis=1), 0.04) + 2e-4 * vtol * vscale)
     assert np.array_equal(eng.download(K.F_MATERIAL), t["material"])
     assert fl.any()
     eng.sync()

@@ -166,10 +166,21 @@ static int ensure_range(tisph_ctx* c) {
 // ------------------------------------------------------------------------------- stages
 static int run_update(tisph_ctx* c) {
     if (c->phase != 0) return fail(TISPH_ERR_INVALID, "UPDATE issued out of order (phase %d)", c->phase);
-    if (c->n == 0) return fail(TISPH_ERR_INVALID, "no particles");
     cudaStream_t st = c->stream;
     c->sp.n = c->n;
     int a = c->cur, b = c->cur ^ 1;
+    if (c->n == 0) {
+        if (!c->sharded) return fail(TISPH_ERR_INVALID, "no particles");
+        // an empty slab (nothing owned, nothing received) still takes part in every exchange
+        CU(cudaMemsetAsync(c->cell_count, 0, sizeof(int) * (size_t)c->ncell, st));
+        CU(cudaMemsetAsync(c->cell_end, 0, sizeof(int) * (size_t)c->ncell, st));
+        CU(cudaMemsetAsync(c->ctr, 0, sizeof(StepCounters), st));
+        CU(cudaMemsetAsync(c->range_dev, 0, 2 * sizeof(int), st));
+        c->range_valid = false;
+        c->in_off = 0; c->appended = false;
+        c->cur = b; c->phase = 1; c->have_sorted = true;
+        return TISPH_OK;
+    }
     int nb_cells = nblocks(c->ncell, SCAN_TILE);
     CU(cudaMemsetAsync(c->cell_count, 0, sizeof(int) * (size_t)c->ncell, st));
     CU(cudaMemsetAsync(c->ctr, 0, sizeof(StepCounters), st));
