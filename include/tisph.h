@@ -109,8 +109,11 @@ typedef enum tisph_param {
     TISPH_P_VOLUME_MODE = 2,
     TISPH_P_DIAGNOSTICS = 3,  /* 1: also store a_nonpressure / a_pressure every step */
     TISPH_P_KERNEL_VARIANT = 4, /* implementation selector for A/B benchmarking (0 = default) */
-    TISPH_P_ID_BASE = 5       /* original id given to the next particle added (auto-increments);
+    TISPH_P_ID_BASE = 5,      /* original id given to the next particle added (auto-increments);
                                  a sharded run sets it so that ids are global */
+    TISPH_P_HAS_BOUNDARY = 6  /* 1: boundary (material 0) particles may reach this context as ghosts
+                                 even though none was added to it (sharded runs with rigid bodies);
+                                 set automatically when a non-fluid particle is added */
 } tisph_param;
 
 const char *tisph_last_error(void);

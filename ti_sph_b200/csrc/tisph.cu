@@ -75,6 +75,7 @@ struct tisph_ctx {
     int snap_n = -1;
     int diagnostics = 0;
     int variant = 0;
+    bool has_boundary = false;         // any non-fluid particle ever added / announced (TISPH_P_HAS_BOUNDARY)
     // slab sharding (tisph_shard.cuh)
     int *rank_key = nullptr;
     bool sharded = false;
@@ -214,7 +215,8 @@ static int run_density(tisph_ctx* c) {
     if (c->phase != 1) return fail(TISPH_ERR_INVALID, "DENSITY issued out of order (phase %d)", c->phase);
     int b = c->cur;
     cudaStream_t st = c->stream;
-    k_density_list<<<c->grid_dl, NB_THREADS, DL_SMEM, st>>>(
+    auto kd = c->sp.volume_mode == 1 ? k_density_list<true> : k_density_list<false>;
+    kd<<<c->grid_dl, NB_THREADS, DL_SMEM, st>>>(
         c->sp, c->cell_end, c->items, c->ctr, c->list_items_cap, c->variant == 1, c->P[b], c->V[b], c->Q[b],
         c->D, c->S, c->ncount, c->Lg, c->Lcnt, c->item_flags, c->fb_d, c->fb_f);
     k_density_fb<<<c->grid_dfb, NB_THREADS, DF_SMEM, st>>>(c->sp, c->cell_end, c->items, c->ctr, c->fb_d,
@@ -231,7 +233,8 @@ static int run_force(tisph_ctx* c) {
     cudaStream_t st = c->stream;
     float4* dnp = c->diagnostics ? c->a_np : nullptr;
     float4* dp = c->diagnostics ? c->a_p : nullptr;
-    k_force_list<<<c->grid_fl, NB_THREADS, FL_SMEM, st>>>(
+    auto kf = c->has_boundary ? k_force_list<true> : k_force_list<false>;
+    kf<<<c->grid_fl, NB_THREADS, FL_SMEM, st>>>(
         c->sp, c->cell_end, c->items, c->ctr, c->P[b], c->V[b], c->Q[b], c->D, c->P[a], c->V[a], c->Q[a],
         c->dvel, dnp, dp, c->Lg, c->Lcnt, c->item_flags);
     k_force_fb<<<c->grid_ffb, NB_THREADS, FF_SMEM, st>>>(
@@ -313,15 +316,17 @@ int tisph_create(const tisph_config* cfg, tisph_ctx** out) {
         A(cudaMemsetAsync(c->keys_sorted, 0, cap * 4, c->stream));
         A(cudaMemsetAsync(c->cell_end, 0, (size_t)c->ncell * 4, c->stream));
         A(cudaMemsetAsync(c->cell_count, 0, (size_t)c->ncell * 4, c->stream));
-        A(cudaFuncSetAttribute(k_density_list, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DL_SMEM));
-        A(cudaFuncSetAttribute(k_force_list, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FL_SMEM));
+        A(cudaFuncSetAttribute(k_density_list<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DL_SMEM));
+        A(cudaFuncSetAttribute(k_density_list<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DL_SMEM));
+        A(cudaFuncSetAttribute(k_force_list<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FL_SMEM));
+        A(cudaFuncSetAttribute(k_force_list<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FL_SMEM));
         A(cudaFuncSetAttribute(k_density_fb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DF_SMEM));
         A(cudaFuncSetAttribute(k_force_fb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FF_SMEM));
         int sms = 0, occ = 0;
         A(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg->device));
-        A(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_density_list, NB_THREADS, DL_SMEM));
+        A(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_density_list<false>, NB_THREADS, DL_SMEM));
         c->grid_dl = sms * (occ > 0 ? occ : 1);
-        A(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_force_list, NB_THREADS, FL_SMEM));
+        A(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_force_list<true>, NB_THREADS, FL_SMEM));
         c->grid_fl = sms * (occ > 0 ? occ : 1);
         A(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_density_fb, NB_THREADS, DF_SMEM));
         c->grid_dfb = sms * (occ > 0 ? occ : 1);
@@ -372,6 +377,8 @@ int tisph_add_particles(tisph_ctx* c, int32_t n, const float* pos, const float* 
     if ((int64_t)c->n + n > c->cap)
         return fail(TISPH_ERR_CAPACITY, "particle_num %d + %d exceeds particle_max_num %d", c->n, n, c->cap);
     if (n == 0) return TISPH_OK;
+    for (int32_t i = 0; i < n && !c->has_boundary; ++i)
+        if (material[i] != MAT_FLUID) c->has_boundary = true;
     int dim = c->cfg.dim;
     cudaStream_t st = c->stream;
     // stage in slices so that the staging buffer (48 B/particle) always suffices
@@ -624,6 +631,7 @@ int tisph_set_param(tisph_ctx* c, int32_t param, double value) {
             return TISPH_OK;
         case TISPH_P_KERNEL_VARIANT: c->variant = (int)value; return TISPH_OK;
         case TISPH_P_ID_BASE: c->id_base = (int)value; return TISPH_OK;
+        case TISPH_P_HAS_BOUNDARY: c->has_boundary = c->has_boundary || value != 0.0; return TISPH_OK;
     }
     return fail(TISPH_ERR_INVALID, "unknown parameter %d", param);
 }
@@ -637,6 +645,7 @@ int tisph_get_param(tisph_ctx* c, int32_t param, double* value) {
         case TISPH_P_DIAGNOSTICS: *value = c->diagnostics; return TISPH_OK;
         case TISPH_P_KERNEL_VARIANT: *value = c->variant; return TISPH_OK;
         case TISPH_P_ID_BASE: *value = c->id_base; return TISPH_OK;
+        case TISPH_P_HAS_BOUNDARY: *value = c->has_boundary; return TISPH_OK;
     }
     return fail(TISPH_ERR_INVALID, "unknown parameter %d", param);
 }

@@ -28,7 +28,7 @@
 namespace tisph {
 
 constexpr int LCAP = 64;               // pending-list slots per thread (shared memory)
-constexpr int CHUNK = 32;              // candidates filtered between drain checks
+constexpr int CHUNK = 32;              // candidates filtered between drain checks (fallback kernels)
 constexpr float FAR = 1e18f;           // padding candidates / idle targets: never within the cutoff
 constexpr int TCAP = 1792;             // candidates of one tile (27 cells x 64 at the reference spacing = 1728)
 constexpr int KCAP = 96;               // neighbour-list entries per thread and item in global memory
@@ -183,13 +183,61 @@ __device__ __forceinline__ int next_item(int* cursor, int* s_slot) {
 }
 
 // =======================================================================================
+// Small PTX helpers of the list kernels
+// =======================================================================================
+__device__ __forceinline__ float rsqrt_approx(float x) {   // one MUFU.RSQ, no denormal fix-up code
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {     // one MUFU.RCP
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+// 32-bit shared-window addressing: the generic->shared conversion is done once per kernel instead
+// of once per access (ptxas re-derives the window base from SR_CgaCtaId inside hot loops otherwise)
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ float lds_f32(uint32_t a) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ float4 lds_f32x4(uint32_t a) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ float2 lds_f32x2(uint32_t a) {
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u16(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_u16(uint32_t a, uint32_t v) {
+    asm volatile("st.shared.u16 [%0], %1;" :: "r"(a), "r"(v) : "memory");
+}
+
+// =======================================================================================
 // Walk 1, list path
 // =======================================================================================
-// tile (pair-SoA, NEGATED coordinates so that x_i - x_j is one packed add):
-//   txy[p] = {-x(2p), -x(2p+1), -y(2p), -y(2p+1)}   tz[p] = {-z(2p), -z(2p+1)}   tm[e] = material
-constexpr size_t DL_SMEM = (size_t)(TCAP / 2) * (sizeof(float4) + sizeof(float2)) + (size_t)TCAP * sizeof(int) +
-                           (size_t)LCAP * NB_THREADS * sizeof(unsigned short);
+// Tile, 32 bytes per candidate PAIR p (coordinates NEGATED so that x_i - x_j is one packed add):
+//   float index 8p+{0,1} = -x   8p+{2,3} = -y   8p+{4,5} = -z   8p+{6,7} = material (i32 bits)
+// A candidate is named by its "pair offset" o = 8p + (0|1) inside the density kernel and by its
+// tile index e = 2p + (0|1) in the lists handed to the force kernel.  Pair TCAP/2 is a dummy pair
+// that is always FAR away: list padding points at it.
+constexpr int DCHUNK = 16;                                    // candidates filtered between drain checks
+constexpr int O_DUMMY = 8 * (TCAP / 2);
+constexpr int E_DUMMY = TCAP;
+constexpr size_t DL_SMEM = (size_t)(TCAP / 2 + 1) * 32 + (size_t)LCAP * NB_THREADS * sizeof(unsigned short);
 
+__device__ __forceinline__ uint32_t o_to_e(uint32_t o) { return ((o >> 2) & ~1u) | (o & 1u); }
+
+template <bool AKINCI>
 __global__ void __launch_bounds__(NB_THREADS, 3)
 k_density_list(SimParams sp, const int* __restrict__ cell_end, const int2* __restrict__ items,
                StepCounters* __restrict__ ctr, int list_items_cap, int all_to_fallback,
@@ -198,12 +246,8 @@ k_density_list(SimParams sp, const int* __restrict__ cell_end, const int2* __res
                uint2* __restrict__ Lg, unsigned short* __restrict__ Lcnt, unsigned char* __restrict__ flags,
                int* __restrict__ fb_d, int* __restrict__ fb_f) {
     extern __shared__ float4 dyn_smem[];
-    float4* txy = dyn_smem;
-    float2* tz = reinterpret_cast<float2*>(dyn_smem + TCAP / 2);
-    int* tm = reinterpret_cast<int*>(tz + TCAP / 2);
-    unsigned short* L = reinterpret_cast<unsigned short*>(tm + TCAP);
-    const float* fxy = reinterpret_cast<const float*>(txy);
-    const float* fz = reinterpret_cast<const float*>(tz);
+    float4* T = dyn_smem;                                                   // [TCAP/2 + 1][2]
+    unsigned short* L = reinterpret_cast<unsigned short*>(dyn_smem + (TCAP / 2 + 1) * 2);
     __shared__ CellRanges R;
     __shared__ float red_w[NB_THREADS];
     __shared__ float red_b[NB_THREADS];
@@ -211,9 +255,11 @@ k_density_list(SimParams sp, const int* __restrict__ cell_end, const int2* __res
     __shared__ int s_slot, s_over;
 
     const int tid = threadIdx.x;
-    const bool akinci = sp.volume_mode == 1;
     const float cut_wide = sp.d2_cut * 1.000001f;       // superset filter; the drain applies the exact test
-    unsigned short* myL = L + tid;
+    const uint32_t sT = smem_u32(T);
+    const uint32_t sL = smem_u32(L) + 2u * tid;         // my pending list: slot k at sL + k * 2 * NB_THREADS
+    for (int k = 0; k < LCAP; ++k) L[k * NB_THREADS + tid] = (unsigned short)O_DUMMY;
+    if (tid < 2) T[TCAP + tid] = tid == 0 ? make_float4(FAR, FAR, FAR, FAR) : make_float4(FAR, FAR, __int_as_float(MAT_FLUID), __int_as_float(MAT_FLUID));
 
     for (;;) {
         const int it = next_item(&ctr->work_d, &s_slot);
@@ -232,24 +278,23 @@ k_density_list(SimParams sp, const int* __restrict__ cell_end, const int2* __res
         const bool keep_list = own && it < list_items_cap;
         if (tid == 0) s_over = keep_list ? 0 : 1;
         // ---- stage the tile ---------------------------------------------------------------
-        const int nchunk = (G.total + CHUNK - 1) / CHUNK;
-        for (int p = tid; p < nchunk * (CHUNK / 2); p += NB_THREADS) {
+        const int nchunk = (G.total + DCHUNK - 1) / DCHUNK;
+        for (int p = tid; p < nchunk * (DCHUNK / 2); p += NB_THREADS) {
             float4 a = make_float4(FAR, FAR, FAR, 0.f), b = a;
             int ma = MAT_FLUID, mb = MAT_FLUID;
             int e = 2 * p;
             if (e < G.total) {
                 int g = tile_to_global(R, e);
                 a = P[g];
-                if (akinci) ma = __float_as_int(Q[g].z);
+                if (AKINCI) ma = __float_as_int(Q[g].z);
             }
             if (e + 1 < G.total) {
                 int g = tile_to_global(R, e + 1);
                 b = P[g];
-                if (akinci) mb = __float_as_int(Q[g].z);
+                if (AKINCI) mb = __float_as_int(Q[g].z);
             }
-            txy[p] = make_float4(-a.x, -b.x, -a.y, -b.y);
-            tz[p] = make_float2(-a.z, -b.z);
-            *reinterpret_cast<int2*>(tm + e) = make_int2(ma, mb);
+            T[2 * p] = make_float4(-a.x, -b.x, -a.y, -b.y);
+            T[2 * p + 1] = make_float4(-a.z, -b.z, __int_as_float(ma), __int_as_float(mb));
         }
         __syncthreads();
         // ---- walk -------------------------------------------------------------------------
@@ -259,49 +304,64 @@ k_density_list(SimParams sp, const int* __restrict__ cell_end, const int2* __res
         const float4 pi = active ? P[i] : make_float4(-FAR, -FAR, -FAR, 0.f);
         const int self_lo = R.gb[4], self_len = R.off[5] - R.off[4];
         const int self_t = (active && i >= self_lo && i < self_lo + self_len) ? R.off[4] + (i - self_lo) : -1;
+        const uint32_t self_o = self_t >= 0 ? (uint32_t)(8 * (self_t >> 1) + (self_t & 1)) : 0xffffffffu;
         const float2 xi2 = make_float2(pi.x, pi.x), yi2 = make_float2(pi.y, pi.y), zi2 = make_float2(pi.z, pi.z);
         float wsum = 0.f, wbsum = 0.f;
-        int cnt = 0, pend = 0, goff = 0;
-        unsigned short* gl = reinterpret_cast<unsigned short*>(Lg + (size_t)it * ITEM_LIST_WORDS);
+        int cnt = 0, pend = 0, gword = 0;          // gword: 4-entry words already written to the global list
+        uint2* gl = Lg + (size_t)it * ITEM_LIST_WORDS + tid;
         for (int ch = split; ch < nchunk; ch += G.nsplit) {
-            const int pb = ch * (CHUNK / 2);
-#pragma unroll 8
-            for (int k = 0; k < CHUNK / 2; ++k) {
-                float4 c = txy[pb + k];
-                float2 cz = tz[pb + k];
+            const int pb = ch * (DCHUNK / 2);
+#pragma unroll
+            for (int k = 0; k < DCHUNK / 2; ++k) {
+                const float4 c = lds_f32x4(sT + 32u * (pb + k));
+                const float2 cz = lds_f32x2(sT + 32u * (pb + k) + 16u);
                 float2 dx = __fadd2_rn(xi2, make_float2(c.x, c.y));
                 float2 dy = __fadd2_rn(yi2, make_float2(c.z, c.w));
                 float2 dz = __fadd2_rn(zi2, cz);
                 float2 s = __ffma2_rn(dz, dz, __ffma2_rn(dy, dy, __fmul2_rn(dx, dx)));
-                if (s.x < cut_wide) { myL[pend * NB_THREADS] = (unsigned short)(2 * (pb + k)); ++pend; }
-                if (s.y < cut_wide) { myL[pend * NB_THREADS] = (unsigned short)(2 * (pb + k) + 1); ++pend; }
+                if (s.x < cut_wide) { sts_u16(sL + pend * (2 * NB_THREADS), 8 * (pb + k)); ++pend; }
+                if (s.y < cut_wide) { sts_u16(sL + pend * (2 * NB_THREADS), 8 * (pb + k) + 1); ++pend; }
             }
             const bool last = ch + G.nsplit >= nchunk;
-            if (last || __any_sync(0xffffffffu, pend > LCAP - CHUNK)) {
-                for (int k = 0; k < pend; ++k) {
-                    const int e = myL[k * NB_THREADS];
-                    const int o = ((e >> 1) << 2) + (e & 1);
-                    const float dx = pi.x + fxy[o], dy = pi.y + fxy[o + 2], dz = pi.z + fz[e];
-                    const float d2 = dist2_exact(dx, dy, dz);
-                    if (keep_list && goff + k < KCAP) {
-                        const int kk = goff + k;       // [word kk/4][thread][kk%4]
-                        gl[((size_t)(kk >> 2) * NB_THREADS + tid) * 4 + (kk & 3)] = (unsigned short)e;
-                    }
-                    if (d2 < sp.d2_cut && e != self_t) {
-                        float r = d2 * rsqrtf(fmaxf(d2, 1e-30f));
-                        float w = spline_w(r * sp.inv_h);
-                        cnt++;
+            if (last || __any_sync(0xffffffffu, pend > LCAP - DCHUNK)) {
+                // ---- drain: whole words of 4 entries; a remainder waits for the next round, the
+                //      final round pads with the dummy candidate.  Branch-free per entry: the self
+                //      entry and slots beyond this lane's count are redirected to the dummy candidate,
+                //      whose distance is FAR (q clamps to 1, W = 0, not counted).
+                const int nd = last ? (pend + 3) & ~3 : pend & ~3;
+                const int lim = last ? pend : nd;                         // entries that are mine to evaluate now
+                const int nd_max = __reduce_max_sync(0xffffffffu, nd);
+                uint2* gp = gl + (size_t)gword * NB_THREADS;
+                const int groom = keep_list ? KCAP / 4 - gword : 0;      // words that still fit the global list
+                for (int k4 = 0; k4 < nd_max; k4 += 4, gp += NB_THREADS) {
+                    uint32_t ew[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        uint32_t o = lds_u16(sL + (k4 + j) * (2 * NB_THREADS));
+                        o = (k4 + j < lim && o != self_o) ? o : (uint32_t)O_DUMMY;
+                        const uint32_t a = sT + 4u * o;
+                        const float dx = pi.x + lds_f32(a), dy = pi.y + lds_f32(a + 8), dz = pi.z + lds_f32(a + 16);
+                        const float d2 = dist2_exact(dx, dy, dz);
+                        const float r = d2 * rsqrt_approx(fmaxf(d2, 1e-30f));
+                        const float w = spline_w(fminf(r * sp.inv_h, 1.0f));
                         wsum += w;
-                        if (tm[e] == MAT_BOUNDARY) wbsum += w;
+                        cnt += d2 < sp.d2_cut ? 1 : 0;
+                        if (AKINCI) wbsum += __float_as_int(lds_f32(a + 24)) == MAT_BOUNDARY ? w : 0.f;
+                        ew[j] = o_to_e(o);
                     }
+                    if (k4 < nd && (k4 >> 2) < groom)
+                        *gp = make_uint2(ew[0] | (ew[1] << 16), ew[2] | (ew[3] << 16));
                 }
-                goff += pend;
-                pend = 0;
+                gword += nd >> 2;
+                // move the remainder (< 4 entries) to the front
+                const int rem = pend - nd;
+                for (int k = 0; k < rem; ++k) sts_u16(sL + k * (2 * NB_THREADS), lds_u16(sL + (nd + k) * (2 * NB_THREADS)));
+                pend = rem > 0 ? rem : 0;
             }
         }
         if (keep_list) {
-            Lcnt[(size_t)it * NB_THREADS + tid] = (unsigned short)min(goff, KCAP);
-            if (goff > KCAP) s_over = 1;               // benign race: every writer stores 1
+            Lcnt[(size_t)it * NB_THREADS + tid] = (unsigned short)min(gword, KCAP / 4);     // in words
+            if (gword > KCAP / 4) s_over = 1;              // benign race: every writer stores 1
         }
         red_w[tid] = wsum;
         red_b[tid] = wbsum;
@@ -325,8 +385,10 @@ k_density_list(SimParams sp, const int* __restrict__ cell_end, const int2* __res
 // =======================================================================================
 // Walk 2, list path: forces + advect + walls
 //   tile record, 36 B per candidate: tP = {x,y,z,psi}  tV = {vx,vy,vz,rho_raw}  tR = p/rho_c^2
+//   slot E_DUMMY is a candidate that is FAR away (list padding points at it)
 // =======================================================================================
-constexpr size_t FL_SMEM = (size_t)TCAP * (2 * sizeof(float4) + sizeof(float));
+constexpr int FTILE = TCAP + 4;
+constexpr size_t FL_SMEM = (size_t)FTILE * (2 * sizeof(float4) + sizeof(float));
 
 __device__ __forceinline__ void stage_force_tile(const CellRanges& R, int tile0, int tile_n, int tile_pad,
                                                  const float4* __restrict__ Pin, const float4* __restrict__ Vin,
@@ -348,6 +410,44 @@ __device__ __forceinline__ void stage_force_tile(const CellRanges& R, int tile0,
     }
 }
 
+// Branch-free pair evaluation of the list kernel.  The self pair and coincident particles give
+// exactly zero (x_ij = 0 and gradW = 0 for r <= 1e-5, sph_basev2.py:53), so no index test is needed;
+// entries outside the cutoff (filter band, list padding) have q clamped to 1, where W and gradW vanish.
+template <bool HAS_BOUNDARY>
+__device__ __forceinline__ void pair_force_bf(const SimParams& sp, float kdw_h, float4 pi, float4 vi, float4 pj,
+                                              float4 vj, float prj, float coh_i, float rho_i, float pr_i,
+                                              float nub_i, ForceAcc& A) {
+    const float dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
+    const float d2 = dist2_exact(dx, dy, dz);
+    const float rinv = rsqrt_approx(fmaxf(d2, 1e-30f));
+    const float r = d2 * rinv;
+    const float q = fminf(r * sp.inv_h, 1.0f);      // beyond the support W = gradW = 0: no mask needed
+    const float f = 1.0f - q;
+    const bool inner = q <= 0.5f;
+    const float dw = inner ? q * fmaf(3.0f, q, -2.0f) : -f * f;              // sph_basev2.py:53-60 (/6k)
+    const float gfac = r > 1e-5f ? dw * rinv * kdw_h : 0.f;                   // gradW = gfac * x_ij
+    const float dot = (vi.x - vj.x) * dx + (vi.y - vj.y) * dy + (vi.z - vj.z) * dz;
+    const float mn = fminf(dot, 0.f) * rcp_approx(d2 + sp.eps_h2);
+    const float psi = pj.w;
+    float cn, cp;
+    {                                                                        // fluid j
+        const float w = sp.k_w * (inner ? fmaf(6.0f * q * q, q - 1.0f, 1.0f) : 2.0f * f * f * f);
+        const float nu = sp.visc_fluid_c * rcp_approx(rho_i + vj.w);          // wcsphv2.py:69
+        cn = psi * (coh_i * w - nu * mn * gfac);                              // :64 + :72-73
+        cp = -psi * (pr_i + prj) * gfac;                                      // sph_basev2.py:71-73
+    }
+    if (HAS_BOUNDARY) {
+        const float vol = -psi;
+        const float cnb = sp.ps_density0 * vol * (-nub_i * mn) * gfac;        // wcsphv2.py:78-80
+        const float cpb = -sp.rho0 * vol * pr_i * gfac;                       // sph_basev2.py:75
+        cn = psi > 0.f ? cn : cnb;
+        cp = psi > 0.f ? cp : cpb;
+    }
+    A.anx = fmaf(cn, dx, A.anx); A.any = fmaf(cn, dy, A.any); A.anz = fmaf(cn, dz, A.anz);
+    A.apx = fmaf(cp, dx, A.apx); A.apy = fmaf(cp, dy, A.apy); A.apz = fmaf(cp, dz, A.apz);
+}
+
+template <bool HAS_BOUNDARY>
 __global__ void __launch_bounds__(NB_THREADS, 3)
 k_force_list(SimParams sp, const int* __restrict__ cell_end, const int2* __restrict__ items,
              StepCounters* __restrict__ ctr, const float4* __restrict__ Pin,
@@ -358,12 +458,20 @@ k_force_list(SimParams sp, const int* __restrict__ cell_end, const int2* __restr
              const unsigned short* __restrict__ Lcnt, const unsigned char* __restrict__ flags) {
     extern __shared__ float4 dyn_smem[];
     float4* tP = dyn_smem;
-    float4* tV = dyn_smem + TCAP;
-    float* tR = reinterpret_cast<float*>(dyn_smem + 2 * TCAP);
+    float4* tV = dyn_smem + FTILE;
+    float* tR = reinterpret_cast<float*>(dyn_smem + 2 * FTILE);
     __shared__ CellRanges R;
     __shared__ float red[6][NB_THREADS];
     __shared__ int s_slot;
     const int tid = threadIdx.x;
+    const uint32_t sP = smem_u32(tP), sR = smem_u32(tR);
+    constexpr uint32_t V_OFF = (uint32_t)FTILE * 16u;
+    const float kdw_h = sp.k_dw * sp.inv_h;
+    if (tid == 0) {
+        tP[E_DUMMY] = make_float4(FAR, FAR, FAR, 1.f);
+        tV[E_DUMMY] = make_float4(0.f, 0.f, 0.f, 1.f);
+        tR[E_DUMMY] = 0.f;
+    }
 
     for (;;) {
         const int it = next_item(&ctr->work_f, &s_slot);
@@ -381,30 +489,25 @@ k_force_list(SimParams sp, const int* __restrict__ cell_end, const int2* __restr
         const float4 di = active ? D[i] : make_float4(1.f, 0.f, 1.f, 0.f);
         const float4 qi = active ? Qin[i] : make_float4(0.f, 0.f, 0.f, 0.f);
         const bool walker = active && __float_as_int(qi.z) == MAT_FLUID;
-        const int self_lo = R.gb[4], self_len = R.off[5] - R.off[4];
-        const int self_t = (active && i >= self_lo && i < self_lo + self_len) ? R.off[4] + (i - self_lo) : -1;
         const float coh_i = 0.01f / pi.w;                         // wcsphv2.py:64
         const float rho_i = di.x, pr_i = di.y;
         const float nub_i = sp.visc_bound_c / (2.0f * rho_i);     // wcsphv2.py:76
         ForceAcc A = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        const int cnt = walker ? (int)Lcnt[(size_t)it * NB_THREADS + tid] : 0;
+        const int nw = walker ? (int)Lcnt[(size_t)it * NB_THREADS + tid] : 0;     // words of 4 entries
         const uint2* gl = Lg + (size_t)it * ITEM_LIST_WORDS + tid;
         __syncthreads();                                   // tile staged
-        uint2 w = cnt > 0 ? gl[0] : make_uint2(0u, 0u);
-        for (int k4 = 0; k4 < cnt; k4 += 4) {
+        uint2 w = nw > 0 ? gl[0] : make_uint2(0u, 0u);
+        for (int k = 0; k < nw; ++k) {
             const uint2 cur = w;
-            if (k4 + 4 < cnt) w = gl[(size_t)((k4 >> 2) + 1) * NB_THREADS];     // prefetch the next 4 entries
-            const int e4[4] = {(int)(cur.x & 0xffffu), (int)(cur.x >> 16), (int)(cur.y & 0xffffu), (int)(cur.y >> 16)};
+            if (k + 1 < nw) w = gl[(size_t)(k + 1) * NB_THREADS];     // prefetch the next 4 entries
+            const uint32_t e4[4] = {cur.x & 0xffffu, cur.x >> 16, cur.y & 0xffffu, cur.y >> 16};
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                const int e = e4[j];
-                if (k4 + j < cnt) {
-                    const float4 pj = tP[e];
-                    const float dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
-                    const float d2 = dist2_exact(dx, dy, dz);
-                    if (d2 < sp.d2_cut && e != self_t)
-                        pair_force(sp, dx, dy, dz, d2, vi, pj.w, tV[e], tR[e], coh_i, rho_i, pr_i, nub_i, A);
-                }
+                const uint32_t a = sP + 16u * e4[j];
+                const float4 pj = lds_f32x4(a);
+                const float4 vj = lds_f32x4(a + V_OFF);
+                const float prj = lds_f32(sR + 4u * e4[j]);
+                pair_force_bf<HAS_BOUNDARY>(sp, kdw_h, pi, vi, pj, vj, prj, coh_i, rho_i, pr_i, nub_i, A);
             }
         }
         red[0][tid] = A.anx; red[1][tid] = A.any; red[2][tid] = A.anz;
@@ -525,9 +628,9 @@ k_force_fb(SimParams sp, const int* __restrict__ cell_end, const int2* __restric
            float4* __restrict__ a_p_out) {
     extern __shared__ float4 dyn_smem[];
     float4* tP = dyn_smem;
-    float4* tV = dyn_smem + TCAP;
-    float* tR = reinterpret_cast<float*>(dyn_smem + 2 * TCAP);
-    unsigned short* L = reinterpret_cast<unsigned short*>(tR + TCAP);
+    float4* tV = dyn_smem + FTILE;
+    float* tR = reinterpret_cast<float*>(dyn_smem + 2 * FTILE);
+    unsigned short* L = reinterpret_cast<unsigned short*>(tR + FTILE);
     __shared__ CellRanges R;
     __shared__ float red[6][NB_THREADS];
     __shared__ int s_slot;

@@ -216,6 +216,8 @@ class ShardedSim:
         self.engine = eng = engine_factory(cfg)
         eng.shard_config(self.plane_lo, self.plane_hi, self.ghost, self.has_left, self.has_right,
                          message_capacity)
+        if scene["rigidBodies"]:
+            eng.set_param(K.P_HAS_BOUNDARY, 1)
         for id0, pos, vel, dens, mat in chunks:
             eng.set_param(K.P_ID_BASE, id0)
             eng.add_particles(pos, vel, dens, np.zeros(len(pos), np.float32), mat)
