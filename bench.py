@@ -241,6 +241,10 @@ def run_gpu(args):
     ms = ev0.elapsed_time(ev1) / args.steps
     launches = eng.launch_count - l0
     stage = eng.stage_times(False)
+    from ti_sph_b200 import _capi as KK
+    items = {"items": int(eng.get_param(KK.P_STAT_ITEMS)),
+             "fallback_density": int(eng.get_param(KK.P_STAT_FALLBACK_DENSITY)),
+             "fallback_force": int(eng.get_param(KK.P_STAT_FALLBACK_FORCE))}
     if world > 1:
         import torch.distributed as dist
         t = torch.tensor([ms], device="cuda")
@@ -303,6 +307,7 @@ def run_gpu(args):
         "traffic": None, "bytes_per_particle": BYTES_FORCE, "launch_ms": stage["force_ms"],
         "step_hbm_frac": BYTES_STEP[args.mode] * n_total / (ms * 1e-3) / 1e9 / hbm_peak / world,
         "stage_ms": {k: stage[k] for k in ("update_ms", "density_ms", "force_ms")},
+        "work_items_last_step": items,
         "note": "the step is FP32-issue-bound at the reference's h = 4 x spacing (1728 candidates, "
                 "~232 neighbours per particle and walk); see DESIGN.md section 5",
     }

@@ -111,9 +111,13 @@ typedef enum tisph_param {
     TISPH_P_KERNEL_VARIANT = 4, /* implementation selector for A/B benchmarking (0 = default) */
     TISPH_P_ID_BASE = 5,      /* original id given to the next particle added (auto-increments);
                                  a sharded run sets it so that ids are global */
-    TISPH_P_HAS_BOUNDARY = 6  /* 1: boundary (material 0) particles may reach this context as ghosts
+    TISPH_P_HAS_BOUNDARY = 6, /* 1: boundary (material 0) particles may reach this context as ghosts
                                  even though none was added to it (sharded runs with rigid bodies);
                                  set automatically when a non-fluid particle is added */
+    /* read-only statistics of the last step (tisph_get_param synchronises the stream) */
+    TISPH_P_STAT_ITEMS = 7,             /* work items (<= 64 targets of one occupied cell) */
+    TISPH_P_STAT_FALLBACK_DENSITY = 8,  /* items whose candidate tile did not fit shared memory */
+    TISPH_P_STAT_FALLBACK_FORCE = 9     /* ... plus items whose neighbour lists overflowed */
 } tisph_param;
 
 const char *tisph_last_error(void);

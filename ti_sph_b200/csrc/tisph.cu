@@ -194,7 +194,7 @@ static int run_update(tisph_ctx* c) {
                                                 c->sharded ? Qin : nullptr, c->rank_key);
     k_reorder<<<nblocks(c->n, 256), 256, 0, st>>>(c->n, c->keys, c->ids, c->rank_key, c->cell_end, Pin, Vin,
                                                   Qin, c->P[b], c->V[b], c->Q[b], c->keys_sorted);
-    k_items<<<nblocks(c->ncell, 256), 256, 0, st>>>(c->ncell, c->sp.walk_key_lo, c->sp.walk_key_hi, c->cell_end,
+    k_items<<<nblocks(c->ncell, 256), 256, 0, st>>>(c->sp, c->sp.walk_key_lo, c->sp.walk_key_hi, c->cell_end,
                                                     c->items, c->ctr);
     c->launches += 7;
     if (c->sharded) {
@@ -295,8 +295,8 @@ int tisph_create(const tisph_config* cfg, tisph_ctx** out) {
     A(dalloc(&c->err_dev, 4));
     {
         int64_t occupied_max = ncell < (int64_t)cap ? ncell : (int64_t)cap;
-        c->items_cap = (int)(occupied_max + (int64_t)cap / 64 + 2);
-        int64_t budget = (int64_t)cap / 32 + 1024;           // items that get a neighbour list (48 KiB each)
+        c->items_cap = (int)(occupied_max + (int64_t)cap / 32 + 2);
+        int64_t budget = (int64_t)cap / 28 + 1024;           // items that get a neighbour list (48 KiB each)
         c->list_items_cap = (int)(budget < c->items_cap ? budget : c->items_cap);
     }
     A(dalloc(&c->items, (size_t)c->items_cap));
@@ -646,6 +646,17 @@ int tisph_get_param(tisph_ctx* c, int32_t param, double* value) {
         case TISPH_P_KERNEL_VARIANT: *value = c->variant; return TISPH_OK;
         case TISPH_P_ID_BASE: *value = c->id_base; return TISPH_OK;
         case TISPH_P_HAS_BOUNDARY: *value = c->has_boundary; return TISPH_OK;
+        case TISPH_P_STAT_ITEMS:
+        case TISPH_P_STAT_FALLBACK_DENSITY:
+        case TISPH_P_STAT_FALLBACK_FORCE: {      // work-item counters of the last step (synchronises)
+            StepCounters h;
+            CU(cudaSetDevice(c->cfg.device));
+            CU(cudaMemcpyAsync(&h, c->ctr, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+            CU(cudaStreamSynchronize(c->stream));
+            *value = param == TISPH_P_STAT_ITEMS ? h.n_items
+                     : param == TISPH_P_STAT_FALLBACK_DENSITY ? h.n_fb_d : h.n_fb_f;
+            return TISPH_OK;
+        }
     }
     return fail(TISPH_ERR_INVALID, "unknown parameter %d", param);
 }

@@ -30,7 +30,7 @@ namespace tisph {
 constexpr int LCAP = 64;               // pending-list slots per thread (shared memory)
 constexpr int CHUNK = 32;              // candidates filtered between drain checks (fallback kernels)
 constexpr float FAR = 1e18f;           // padding candidates / idle targets: never within the cutoff
-constexpr int TCAP = 1792;             // candidates of one tile (27 cells x 64 at the reference spacing = 1728)
+constexpr int TCAP = 1792;             // candidates of one shared-memory tile (27 cells x 64 at the reference spacing = 1728)
 constexpr int KCAP = 96;               // neighbour-list entries per thread and item in global memory
 constexpr int ITEM_LIST_WORDS = NB_THREADS * KCAP / 4;   // uint2 words of one item's lists
 
@@ -42,14 +42,36 @@ struct StepCounters {
     int pad;
 };
 
-// item = {cell, first target of the pass relative to the cell's first particle}
+// number of candidates in the 27-cell neighbourhood of cell c (9 contiguous ranges, see above)
+__device__ __forceinline__ int cell_tile_total(const SimParams& sp, const int* __restrict__ cell_end, int c) {
+    const int cz = c % sp.gz, cy = (c / sp.gz) % sp.gy, cx = c / (sp.gz * sp.gy);
+    const int zlo = max(cz - 1, 0), zhi = min(cz + 1, sp.gz - 1);
+    int total = 0;
+    for (int dx = -1; dx <= 1; ++dx)
+        for (int dy = -1; dy <= 1; ++dy) {
+            const int x = cx + dx, y = cy + dy;
+            if (x < 0 || x >= sp.gx || y < 0 || y >= sp.gy) continue;
+            const int clo = (x * sp.gy + y) * sp.gz + zlo;
+            total += cell_end[clo + (zhi - zlo)] - cell_end[max(clo - 1, 0)];
+        }
+    return total;
+}
+
+// item = {cell, first target relative to the cell's first particle | ITEM_HALF}.  An item holds up
+// to 64 targets (4 splits per target) or, where the neighbourhood is dense, 32 (8 splits), which
+// keeps the per-thread neighbour lists within KCAP.
+constexpr int ITEM_HALF = 1 << 30;
+constexpr int DENSE_TOTAL = 1920;
+
 __global__ void __launch_bounds__(256)
-k_items(int ncell, int key_lo, int key_hi, const int* __restrict__ cell_end, int2* __restrict__ items,
+k_items(SimParams sp, int key_lo, int key_hi, const int* __restrict__ cell_end, int2* __restrict__ items,
         StepCounters* __restrict__ ctr) {
     int c = blockIdx.x * blockDim.x + threadIdx.x;
     int cnt = 0;
-    if (c < ncell && c >= key_lo && c < key_hi) cnt = cell_end[c] - cell_start(cell_end, c);
-    int ni = cnt == 0 ? 0 : (cnt + 63) >> 6;
+    if (c < sp.ncell && c >= key_lo && c < key_hi) cnt = cell_end[c] - cell_start(cell_end, c);
+    int per = 64;
+    if (cnt > 64 || (cnt > 32 && cell_tile_total(sp, cell_end, c) > DENSE_TOTAL)) per = 32;
+    int ni = (cnt + per - 1) / per;
     // warp-aggregated reservation keeps the list roughly in cell order (L2 locality of the walks)
     int lane = threadIdx.x & 31;
     int inc = warp_inclusive_scan(ni, lane);
@@ -57,7 +79,7 @@ k_items(int ncell, int key_lo, int key_hi, const int* __restrict__ cell_end, int
     int base = 0;
     if (lane == 31 && tot > 0) base = atomicAdd(&ctr->n_items, tot);
     base = __shfl_sync(0xffffffffu, base, 31) + inc - ni;
-    for (int k = 0; k < ni; ++k) items[base + k] = make_int2(c, k << 6);
+    for (int k = 0; k < ni; ++k) items[base + k] = make_int2(c, (k * per) | (per == 32 ? ITEM_HALF : 0));
 }
 
 struct ItemGeom {
@@ -70,8 +92,8 @@ __device__ __forceinline__ void item_setup(const SimParams& sp, const int* __res
     G.c = item.x;
     G.tb = cell_start(cell_end, G.c);
     G.te = cell_end[G.c];
-    G.i0 = G.tb + item.y;
-    G.nT = min(G.te - G.i0, 64);
+    G.i0 = G.tb + (item.y & ~ITEM_HALF);
+    G.nT = min(G.te - G.i0, (item.y & ITEM_HALF) ? 32 : 64);
     G.tl = G.nT <= 32 ? 32 : 64;
     G.nsplit = NB_THREADS / G.tl;
     compute_cell_ranges(sp, cell_end, G.c, R);
@@ -233,9 +255,39 @@ __device__ __forceinline__ void sts_u16(uint32_t a, uint32_t v) {
 constexpr int DCHUNK = 16;                                    // candidates filtered between drain checks
 constexpr int O_DUMMY = 8 * (TCAP / 2);
 constexpr int E_DUMMY = TCAP;
+constexpr uint32_t E_NONE = 0xffffu;                          // list entry that names no candidate (padding)
+constexpr int MAX_TOTAL = 0xfff0;                             // candidate indices of an item must fit 16 bits
 constexpr size_t DL_SMEM = (size_t)(TCAP / 2 + 1) * 32 + (size_t)LCAP * NB_THREADS * sizeof(unsigned short);
 
 __device__ __forceinline__ uint32_t o_to_e(uint32_t o) { return ((o >> 2) & ~1u) | (o & 1u); }
+
+// Split s of an item walks the candidate pairs s, s + nsplit, s + 2 nsplit, ... of the tile (pair-wise
+// interleave keeps the splits' survivor counts balanced on lattice-like states).  In shared memory
+// the pairs of one split are stored contiguously -- pair p lives at slot (p % nsplit) * S + p / nsplit,
+// S = TCAP/2/nsplit -- so that the filter reads consecutive slots and the later random gathers of a
+// warp (all lanes of a warp belong to one split) spread over all banks.
+__device__ __forceinline__ int pair_slot(int p, int nsplit) {       // nsplit is 4 or 8
+    const int ls = nsplit == 4 ? 2 : 3;
+    return (p & (nsplit - 1)) * ((TCAP / 2) >> ls) + (p >> ls);
+}
+// swizzled slot of tile candidate e (used as the candidate's name in the neighbour lists)
+__device__ __forceinline__ int cand_slot(int e, int nsplit) { return 2 * pair_slot(e >> 1, nsplit) + (e & 1); }
+
+// Filter 8 consecutive pair slots and push the survivors' pair offsets.
+__device__ __forceinline__ void filter8(uint32_t a0, uint32_t o0, float2 xi2, float2 yi2, float2 zi2,
+                                        float cut_wide, uint32_t sL, int& pend) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const float4 c = lds_f32x4(a0 + 32u * k);
+        const float2 cz = lds_f32x2(a0 + 32u * k + 16u);
+        float2 dx = __fadd2_rn(xi2, make_float2(c.x, c.y));
+        float2 dy = __fadd2_rn(yi2, make_float2(c.z, c.w));
+        float2 dz = __fadd2_rn(zi2, cz);
+        float2 s = __ffma2_rn(dz, dz, __ffma2_rn(dy, dy, __fmul2_rn(dx, dx)));
+        if (s.x < cut_wide) { sts_u16(sL + pend * (2 * NB_THREADS), o0 + 8u * k); ++pend; }
+        if (s.y < cut_wide) { sts_u16(sL + pend * (2 * NB_THREADS), o0 + 8u * k + 1u); ++pend; }
+    }
+}
 
 template <bool AKINCI>
 __global__ void __launch_bounds__(NB_THREADS, 3)
@@ -266,7 +318,7 @@ k_density_list(SimParams sp, const int* __restrict__ cell_end, const int2* __res
         if (it >= ctr->n_items) break;
         ItemGeom G;
         item_setup(sp, cell_end, items[it], R, G);
-        if (G.total > TCAP || all_to_fallback) {        // tile does not fit: self-contained fallback kernels
+        if (G.total > MAX_TOTAL || all_to_fallback) {   // candidate indices must fit 16 bits
             if (tid == 0) {
                 flags[it] = 2;
                 fb_d[atomicAdd(&ctr->n_fb_d, 1)] = it;
@@ -277,87 +329,89 @@ k_density_list(SimParams sp, const int* __restrict__ cell_end, const int2* __res
         const bool own = G.c >= sp.own_key_lo && G.c < sp.own_key_hi;   // ghost cells get no force walk
         const bool keep_list = own && it < list_items_cap;
         if (tid == 0) s_over = keep_list ? 0 : 1;
-        // ---- stage the tile ---------------------------------------------------------------
-        const int nchunk = (G.total + DCHUNK - 1) / DCHUNK;
-        for (int p = tid; p < nchunk * (DCHUNK / 2); p += NB_THREADS) {
-            float4 a = make_float4(FAR, FAR, FAR, 0.f), b = a;
-            int ma = MAT_FLUID, mb = MAT_FLUID;
-            int e = 2 * p;
-            if (e < G.total) {
-                int g = tile_to_global(R, e);
-                a = P[g];
-                if (AKINCI) ma = __float_as_int(Q[g].z);
-            }
-            if (e + 1 < G.total) {
-                int g = tile_to_global(R, e + 1);
-                b = P[g];
-                if (AKINCI) mb = __float_as_int(Q[g].z);
-            }
-            T[2 * p] = make_float4(-a.x, -b.x, -a.y, -b.y);
-            T[2 * p + 1] = make_float4(-a.z, -b.z, __int_as_float(ma), __int_as_float(mb));
-        }
-        __syncthreads();
-        // ---- walk -------------------------------------------------------------------------
         const int t_local = tid % G.tl, split = tid / G.tl;
         const int i = G.i0 + t_local;
         const bool active = t_local < G.nT;
         const float4 pi = active ? P[i] : make_float4(-FAR, -FAR, -FAR, 0.f);
         const int self_lo = R.gb[4], self_len = R.off[5] - R.off[4];
         const int self_t = (active && i >= self_lo && i < self_lo + self_len) ? R.off[4] + (i - self_lo) : -1;
-        const uint32_t self_o = self_t >= 0 ? (uint32_t)(8 * (self_t >> 1) + (self_t & 1)) : 0xffffffffu;
         const float2 xi2 = make_float2(pi.x, pi.x), yi2 = make_float2(pi.y, pi.y), zi2 = make_float2(pi.z, pi.z);
         float wsum = 0.f, wbsum = 0.f;
         int cnt = 0, pend = 0, gword = 0;          // gword: 4-entry words already written to the global list
         uint2* gl = Lg + (size_t)it * ITEM_LIST_WORDS + tid;
-        for (int ch = split; ch < nchunk; ch += G.nsplit) {
-            const int pb = ch * (DCHUNK / 2);
-#pragma unroll
-            for (int k = 0; k < DCHUNK / 2; ++k) {
-                const float4 c = lds_f32x4(sT + 32u * (pb + k));
-                const float2 cz = lds_f32x2(sT + 32u * (pb + k) + 16u);
-                float2 dx = __fadd2_rn(xi2, make_float2(c.x, c.y));
-                float2 dy = __fadd2_rn(yi2, make_float2(c.z, c.w));
-                float2 dz = __fadd2_rn(zi2, cz);
-                float2 s = __ffma2_rn(dz, dz, __ffma2_rn(dy, dy, __fmul2_rn(dx, dx)));
-                if (s.x < cut_wide) { sts_u16(sL + pend * (2 * NB_THREADS), 8 * (pb + k)); ++pend; }
-                if (s.y < cut_wide) { sts_u16(sL + pend * (2 * NB_THREADS), 8 * (pb + k) + 1); ++pend; }
-            }
-            const bool last = ch + G.nsplit >= nchunk;
-            if (last || __any_sync(0xffffffffu, pend > LCAP - DCHUNK)) {
-                // ---- drain: whole words of 4 entries; a remainder waits for the next round, the
-                //      final round pads with the dummy candidate.  Branch-free per entry: the self
-                //      entry and slots beyond this lane's count are redirected to the dummy candidate,
-                //      whose distance is FAR (q clamps to 1, W = 0, not counted).
-                const int nd = last ? (pend + 3) & ~3 : pend & ~3;
-                const int lim = last ? pend : nd;                         // entries that are mine to evaluate now
-                const int nd_max = __reduce_max_sync(0xffffffffu, nd);
-                uint2* gp = gl + (size_t)gword * NB_THREADS;
-                const int groom = keep_list ? KCAP / 4 - gword : 0;      // words that still fit the global list
-                for (int k4 = 0; k4 < nd_max; k4 += 4, gp += NB_THREADS) {
-                    uint32_t ew[4];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        uint32_t o = lds_u16(sL + (k4 + j) * (2 * NB_THREADS));
-                        o = (k4 + j < lim && o != self_o) ? o : (uint32_t)O_DUMMY;
-                        const uint32_t a = sT + 4u * o;
-                        const float dx = pi.x + lds_f32(a), dy = pi.y + lds_f32(a + 8), dz = pi.z + lds_f32(a + 16);
-                        const float d2 = dist2_exact(dx, dy, dz);
-                        const float r = d2 * rsqrt_approx(fmaxf(d2, 1e-30f));
-                        const float w = spline_w(fminf(r * sp.inv_h, 1.0f));
-                        wsum += w;
-                        cnt += d2 < sp.d2_cut ? 1 : 0;
-                        if (AKINCI) wbsum += __float_as_int(lds_f32(a + 24)) == MAT_BOUNDARY ? w : 0.f;
-                        ew[j] = o_to_e(o);
-                    }
-                    if (k4 < nd && (k4 >> 2) < groom)
-                        *gp = make_uint2(ew[0] | (ew[1] << 16), ew[2] | (ew[3] << 16));
+        // the candidates are walked tile by tile (one tile at the reference spacing)
+        for (int tile0 = 0; tile0 < G.total; tile0 += TCAP) {
+            const int tile_n = min(TCAP, G.total - tile0);
+            if (tile0 > 0) __syncthreads();                       // previous tile fully walked
+            // ---- stage the tile -------------------------------------------------------------
+            const int group = DCHUNK * G.nsplit;                  // candidates per round of all splits
+            const int npair = (tile_n + group - 1) / group * (group / 2);      // staged pairs (padded with FAR)
+            for (int p = tid; p < npair; p += NB_THREADS) {
+                float4 a = make_float4(FAR, FAR, FAR, 0.f), b = a;
+                int ma = MAT_FLUID, mb = MAT_FLUID;
+                int e = 2 * p;
+                if (e < tile_n) {
+                    int g = tile_to_global(R, tile0 + e);
+                    a = P[g];
+                    if (AKINCI) ma = __float_as_int(Q[g].z);
                 }
-                gword += nd >> 2;
-                // move the remainder (< 4 entries) to the front
-                const int rem = pend - nd;
-                for (int k = 0; k < rem; ++k) sts_u16(sL + k * (2 * NB_THREADS), lds_u16(sL + (nd + k) * (2 * NB_THREADS)));
-                pend = rem > 0 ? rem : 0;
+                if (e + 1 < tile_n) {
+                    int g = tile_to_global(R, tile0 + e + 1);
+                    b = P[g];
+                    if (AKINCI) mb = __float_as_int(Q[g].z);
+                }
+                const int slot = pair_slot(p, G.nsplit);
+                T[2 * slot] = make_float4(-a.x, -b.x, -a.y, -b.y);
+                T[2 * slot + 1] = make_float4(-a.z, -b.z, __int_as_float(ma), __int_as_float(mb));
             }
+            __syncthreads();
+            // ---- walk -----------------------------------------------------------------------
+            const int self_r = self_t - tile0;
+            const uint32_t self_o = (self_r >= 0 && self_r < TCAP)
+                                        ? (uint32_t)(8 * pair_slot(self_r >> 1, G.nsplit) + (self_r & 1)) : 0xffffffffu;
+            const int mtot = npair / G.nsplit;                    // my pairs in this tile: split, split + nsplit, ...
+            for (int m0 = 0; m0 < mtot; m0 += DCHUNK / 2) {
+                const uint32_t p0 = (uint32_t)(split * ((TCAP / 2) >> (G.nsplit == 4 ? 2 : 3)) + m0);   // first pair slot of the chunk
+                filter8(sT + 32u * p0, 8u * p0, xi2, yi2, zi2, cut_wide, sL, pend);
+                const bool last = m0 + DCHUNK / 2 >= mtot;        // my last chunk of this tile
+                if (last || __any_sync(0xffffffffu, pend > LCAP - DCHUNK)) {
+                    // ---- drain: whole words of 4 entries; a remainder waits for the next round, the
+                    //      last round of a tile pads with the dummy candidate.  Branch-free per entry:
+                    //      the self entry and slots beyond this lane's count are redirected to the
+                    //      dummy candidate, whose distance is FAR (q clamps to 1, W = 0, not counted).
+                    const int nd = last ? (pend + 3) & ~3 : pend & ~3;
+                    const int lim = last ? pend : nd;                     // entries that are mine to evaluate now
+                    const int nd_max = __reduce_max_sync(0xffffffffu, nd);
+                    uint2* gp = gl + (size_t)gword * NB_THREADS;
+                    const int groom = keep_list ? KCAP / 4 - gword : 0;   // words that still fit the global list
+                    for (int k4 = 0; k4 < nd_max; k4 += 4, gp += NB_THREADS) {
+                        uint32_t ew[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            uint32_t o = lds_u16(sL + (k4 + j) * (2 * NB_THREADS));
+                            const bool real = k4 + j < lim && o != self_o;
+                            o = real ? o : (uint32_t)O_DUMMY;
+                            const uint32_t a = sT + 4u * o;
+                            const float dx = pi.x + lds_f32(a), dy = pi.y + lds_f32(a + 8), dz = pi.z + lds_f32(a + 16);
+                            const float d2 = dist2_exact(dx, dy, dz);
+                            const float r = d2 * rsqrt_approx(fmaxf(d2, 1e-30f));
+                            const float w = spline_w(fminf(r * sp.inv_h, 1.0f));
+                            wsum += w;
+                            cnt += d2 < sp.d2_cut ? 1 : 0;
+                            if (AKINCI) wbsum += __float_as_int(lds_f32(a + 24)) == MAT_BOUNDARY ? w : 0.f;
+                            ew[j] = real ? (uint32_t)tile0 + o_to_e(o) : E_NONE;
+                        }
+                        if (k4 < nd && (k4 >> 2) < groom)
+                            *gp = make_uint2(ew[0] | (ew[1] << 16), ew[2] | (ew[3] << 16));
+                    }
+                    gword += nd >> 2;
+                    // move the remainder (< 4 entries) to the front
+                    const int rem = pend - nd;
+                    for (int k = 0; k < rem; ++k) sts_u16(sL + k * (2 * NB_THREADS), lds_u16(sL + (nd + k) * (2 * NB_THREADS)));
+                    pend = rem > 0 ? rem : 0;
+                }
+            }
+            // every split drains completely at the end of a tile: pend == 0 at every tile boundary
         }
         if (keep_list) {
             Lcnt[(size_t)it * NB_THREADS + tid] = (unsigned short)min(gword, KCAP / 4);     // in words
@@ -390,7 +444,9 @@ k_density_list(SimParams sp, const int* __restrict__ cell_end, const int2* __res
 constexpr int FTILE = TCAP + 4;
 constexpr size_t FL_SMEM = (size_t)FTILE * (2 * sizeof(float4) + sizeof(float));
 
-__device__ __forceinline__ void stage_force_tile(const CellRanges& R, int tile0, int tile_n, int tile_pad,
+// nsplit > 0: candidate e goes to slot cand_slot(e, nsplit) (the name it has in the neighbour lists);
+// nsplit == 0: slot e (fallback kernel)
+__device__ __forceinline__ void stage_force_tile(const CellRanges& R, int tile0, int tile_n, int tile_pad, int nsplit,
                                                  const float4* __restrict__ Pin, const float4* __restrict__ Vin,
                                                  const float4* __restrict__ Qin, const float4* __restrict__ D,
                                                  float4* tP, float4* tV, float* tR) {
@@ -406,7 +462,8 @@ __device__ __forceinline__ void stage_force_tile(const CellRanges& R, int tile0,
             v.w = d.x;
             pr = d.y;
         }
-        tP[e] = p; tV[e] = v; tR[e] = pr;
+        const int slot = nsplit > 0 ? cand_slot(e, nsplit) : e;
+        tP[slot] = p; tV[slot] = v; tR[slot] = pr;
     }
 }
 
@@ -480,7 +537,6 @@ k_force_list(SimParams sp, const int* __restrict__ cell_end, const int2* __restr
         if (items[it].x < sp.own_key_lo || items[it].x >= sp.own_key_hi) continue;   // ghost cell: not advanced here
         ItemGeom G;
         item_setup(sp, cell_end, items[it], R, G);
-        stage_force_tile(R, 0, G.total, G.total, Pin, Vin, Qin, D, tP, tV, tR);
         const int t_local = tid % G.tl, split = tid / G.tl;
         const int i = G.i0 + t_local;
         const bool active = t_local < G.nT;
@@ -495,19 +551,53 @@ k_force_list(SimParams sp, const int* __restrict__ cell_end, const int2* __restr
         ForceAcc A = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         const int nw = walker ? (int)Lcnt[(size_t)it * NB_THREADS + tid] : 0;     // words of 4 entries
         const uint2* gl = Lg + (size_t)it * ITEM_LIST_WORDS + tid;
-        __syncthreads();                                   // tile staged
         uint2 w = nw > 0 ? gl[0] : make_uint2(0u, 0u);
-        for (int k = 0; k < nw; ++k) {
-            const uint2 cur = w;
-            if (k + 1 < nw) w = gl[(size_t)(k + 1) * NB_THREADS];     // prefetch the next 4 entries
-            const uint32_t e4[4] = {cur.x & 0xffffu, cur.x >> 16, cur.y & 0xffffu, cur.y >> 16};
+        if (G.total <= TCAP) {
+            // ---- one tile (the common case): replay the whole list
+            stage_force_tile(R, 0, G.total, G.total, G.nsplit, Pin, Vin, Qin, D, tP, tV, tR);
+            __syncthreads();                                   // tile staged
+            for (int k = 0; k < nw; ++k) {
+                const uint2 cur = w;
+                if (k + 1 < nw) w = gl[(size_t)(k + 1) * NB_THREADS];     // prefetch the next 4 entries
+                const uint32_t e4[4] = {cur.x & 0xffffu, cur.x >> 16, cur.y & 0xffffu, cur.y >> 16};
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const uint32_t a = sP + 16u * e4[j];
-                const float4 pj = lds_f32x4(a);
-                const float4 vj = lds_f32x4(a + V_OFF);
-                const float prj = lds_f32(sR + 4u * e4[j]);
-                pair_force_bf<HAS_BOUNDARY>(sp, kdw_h, pi, vi, pj, vj, prj, coh_i, rho_i, pr_i, nub_i, A);
+                for (int j = 0; j < 4; ++j) {
+                    const uint32_t e = min(e4[j], (uint32_t)E_DUMMY);      // E_NONE -> dummy candidate
+                    const uint32_t a = sP + 16u * e;
+                    const float4 pj = lds_f32x4(a);
+                    const float4 vj = lds_f32x4(a + V_OFF);
+                    const float prj = lds_f32(sR + 4u * e);
+                    pair_force_bf<HAS_BOUNDARY>(sp, kdw_h, pi, vi, pj, vj, prj, coh_i, rho_i, pr_i, nub_i, A);
+                }
+            }
+        } else {
+            // ---- several tiles: every list is ascending, so a tile's entries are one run of it;
+            //      a word that straddles a tile boundary is replayed in both tiles with the
+            //      foreign entries redirected to the dummy candidate
+            int k = 0;
+            for (int tile0 = 0; tile0 < G.total; tile0 += TCAP) {
+                const int tile_n = min(TCAP, G.total - tile0);
+                if (tile0 > 0) __syncthreads();
+                stage_force_tile(R, tile0, tile_n, tile_n, G.nsplit, Pin, Vin, Qin, D, tP, tV, tR);
+                __syncthreads();
+                while (k < nw) {
+                    const uint32_t e4[4] = {w.x & 0xffffu, w.x >> 16, w.y & 0xffffu, w.y >> 16};
+                    bool done = true;                          // every real entry of the word lies below the tile's end
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const uint32_t rel = e4[j] - (uint32_t)tile0;
+                        const uint32_t e = rel < (uint32_t)TCAP ? rel : (uint32_t)E_DUMMY;
+                        done = done && (e4[j] == E_NONE || e4[j] < (uint32_t)(tile0 + TCAP));
+                        const uint32_t a = sP + 16u * e;
+                        const float4 pj = lds_f32x4(a);
+                        const float4 vj = lds_f32x4(a + V_OFF);
+                        const float prj = lds_f32(sR + 4u * e);
+                        pair_force_bf<HAS_BOUNDARY>(sp, kdw_h, pi, vi, pj, vj, prj, coh_i, rho_i, pr_i, nub_i, A);
+                    }
+                    if (!done) break;
+                    ++k;
+                    if (k < nw) w = gl[(size_t)k * NB_THREADS];
+                }
             }
         }
         red[0][tid] = A.anx; red[1][tid] = A.any; red[2][tid] = A.anz;
@@ -663,7 +753,7 @@ k_force_fb(SimParams sp, const int* __restrict__ cell_end, const int2* __restric
             const int tile_n = min(TCAP, G.total - tile0);
             const int tile_pad = (tile_n + CHUNK - 1) & ~(CHUNK - 1);
             __syncthreads();
-            stage_force_tile(R, tile0, tile_n, tile_pad, Pin, Vin, Qin, D, tP, tV, tR);
+            stage_force_tile(R, tile0, tile_n, tile_pad, 0, Pin, Vin, Qin, D, tP, tV, tR);
             __syncthreads();
             const int self_t = self_e - tile0;
             int pend = 0;
