@@ -28,7 +28,17 @@ UNIT = "particle-updates/s"
 # algorithmic HBM bytes per particle-step
 BYTES_STEP = {"reference": 170.0, "summed": 186.0}
 BYTES_FORCE = 68.0      # fused forces+advect+walls: R {x,v,mass,volume,material,rho,p} 44 + W {x,v} 24
-BYTES_DENSITY = {"reference": 8.0, "summed": 24.0}
+BYTES_DENSITY = {"reference": 8.0, "summed": 24.0}     # R x 12 + mass 4, W rho 4 + p 4 (rho = mass W(0) needs no x)
+
+
+def measured_traffic(workload, kernel):
+    """dram__bytes_read+write per launch of `kernel` from the committed ncu --set full capture
+    (profiles/r01_traffic.json, written by scripts/ncu_summary.py), or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+            return json.load(f).get(workload, {}).get(kernel)
+    except Exception:
+        return None
 
 
 def log(*a):
@@ -55,7 +65,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(gpu_index), f"--query-gpu={self.Q}",
-                 "--format=csv,noheader,nounits", "-lms", "100"],
+                 "--format=csv,noheader,nounits", "-lms", "20"],
                 stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
@@ -297,19 +307,30 @@ def run_gpu(args):
 
     if rank != 0:
         return
-    # ---- roofline of the dominant kernel (k_force), measured live with CUDA events --------
+    # ---- roofline of the dominant kernel, measured live with CUDA events on the engine's stream ----
     n_local = eng.particle_num
-    force_s = stage["force_ms"] * 1e-3
-    achieved = BYTES_FORCE * n_local / force_s / 1e9 if force_s > 0 else 0.0
+    cand = {"density": ("k_density_list (+k_density_fb): boundary volume, density summation, clamp, Tait EOS",
+                        BYTES_DENSITY[args.mode], stage["density_ms"], "k_density_list"),
+            "force": ("k_force_list (+k_force_fb): non-pressure + pressure forces, advect, walls",
+                      BYTES_FORCE, stage["force_ms"], "k_force_list")}
+    dom = max(cand, key=lambda k: cand[k][2])
+    kname, kbytes, kms, ktag = cand[dom]
+    achieved = kbytes * n_local / (kms * 1e-3) / 1e9 if kms > 0 else 0.0
+    traffic = measured_traffic(args.workload, ktag)
     roofline = {
-        "bound": "hbm", "kernel": "k_force (forces+advect+walls)", "achieved": achieved,
+        "bound": "hbm", "kernel": kname, "achieved": achieved,
         "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "peak_kind": peak_kind,
-        "traffic": None, "bytes_per_particle": BYTES_FORCE, "launch_ms": stage["force_ms"],
+        "traffic": traffic, "bytes_per_particle": kbytes, "launch_ms": kms,
         "step_hbm_frac": BYTES_STEP[args.mode] * n_total / (ms * 1e-3) / 1e9 / hbm_peak / world,
         "stage_ms": {k: stage[k] for k in ("update_ms", "density_ms", "force_ms")},
+        "stage_hbm_frac": {"update": (16 + 2 + 76) * n_local / max(stage["update_ms"], 1e-9) / 1e6 / hbm_peak,
+                           "density": BYTES_DENSITY[args.mode] * n_local / max(stage["density_ms"], 1e-9) / 1e6 / hbm_peak,
+                           "force": BYTES_FORCE * n_local / max(stage["force_ms"], 1e-9) / 1e6 / hbm_peak},
         "work_items_last_step": items,
-        "note": "the step is FP32-issue-bound at the reference's h = 4 x spacing (1728 candidates, "
-                "~232 neighbours per particle and walk); see DESIGN.md section 5",
+        "traffic_note": "dram read+write bytes per launch, ncu --set full capture of this workload (profiles/r01_traffic.json)",
+        "note": "both walks are bound by FP32 instruction issue and shared-memory gathers, not HBM: at the "
+                "reference's h = 4 x spacing every particle filters 1728 candidates and evaluates ~243 pairs per "
+                "walk (ncu: issue-active 72-77 %, shared wavefronts 70-75 %); see DESIGN.md section 5",
     }
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
