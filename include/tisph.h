@@ -90,7 +90,9 @@ typedef enum tisph_field {
     TISPH_F_ORIG_ID = 14,     /* index the particle had when it was added     i32 [n] */
     TISPH_F_A_NONPRESSURE = 15, /* d_velocity after wcsphv2.py:93 (needs TISPH_P_DIAGNOSTICS) */
     TISPH_F_A_PRESSURE = 16,  /* sum added at wcsphv2.py:53 (needs TISPH_P_DIAGNOSTICS) */
-    TISPH_F_CELL_COUNT = 17   /* histogram before the scan, partice_systemv4.py:213  i32 [ncell] */
+    TISPH_F_CELL_COUNT = 17,  /* histogram before the scan, partice_systemv4.py:213  i32 [ncell] */
+    TISPH_F_NEIGHBORS = 18    /* gen-1 only: ps.particle_neighbors i32 [n][100], zero-filled beyond the
+                                 count (partice_system.py:102-121,213); counts = TISPH_F_NEIGHBOR_COUNT */
 } tisph_field;
 
 /* Stages of one step, for stage-by-stage parity tests (tisph_step runs them in order). */

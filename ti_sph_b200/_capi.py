@@ -35,7 +35,7 @@ class Config(C.Structure):
 # enum tisph_field
 F_X, F_V, F_MASS, F_VOLUME, F_DENSITY, F_PRESSURE, F_MATERIAL, F_COLOR, F_GRID_IDS, \
     F_GRID_PARTICLES_NUM, F_D_VELOCITY, F_DENSITY_SUM, F_DENSITY_RAW, F_NEIGHBOR_COUNT, \
-    F_ORIG_ID, F_A_NONPRESSURE, F_A_PRESSURE, F_CELL_COUNT = range(18)
+    F_ORIG_ID, F_A_NONPRESSURE, F_A_PRESSURE, F_CELL_COUNT, F_NEIGHBORS = range(19)
 # enum tisph_stage
 STAGE_UPDATE, STAGE_DENSITY, STAGE_FORCE_ADVECT = range(3)
 # enum tisph_param

@@ -13,6 +13,7 @@
 #include "tisph_kernels.cuh"
 #include "tisph_walk.cuh"
 #include "tisph_shard.cuh"
+#include "tisph_gen1.cuh"
 
 using namespace tisph;
 
@@ -75,7 +76,8 @@ struct tisph_ctx {
     int snap_n = -1;
     int diagnostics = 0;
     int variant = 0;
-    bool has_boundary = false;         // any non-fluid particle ever added / announced (TISPH_P_HAS_BOUNDARY)
+    bool has_boundary = false;
+    int *nbr = nullptr, *nbr_num = nullptr;     // gen-1: particle_neighbors[cap][100], particle_neighbors_num         // any non-fluid particle ever added / announced (TISPH_P_HAS_BOUNDARY)
     // slab sharding (tisph_shard.cuh)
     int *rank_key = nullptr;
     bool sharded = false;
@@ -165,8 +167,33 @@ static int ensure_range(tisph_ctx* c) {
 }
 
 // ------------------------------------------------------------------------------- stages
+// gen-1: ps.init() = clear + allocate_particles_to_grid + search_neighbors (partice_system.py:211-215)
+static int run_update_gen1(tisph_ctx* c) {
+    if (c->n == 0) return fail(TISPH_ERR_INVALID, "no particles");
+    cudaStream_t st = c->stream;
+    c->sp.n = c->n;
+    int a = c->cur;
+    int nb_cells = nblocks(c->ncell, SCAN_TILE);
+    CU(cudaMemsetAsync(c->cell_count, 0, sizeof(int) * (size_t)c->ncell, st));
+    CU(cudaMemsetAsync(c->nbr, 0, sizeof(int) * (size_t)c->n * G1_MAX_NEIGHBORS, st));   // particle_neighbors.fill(0)
+    k_bin<<<nblocks(c->n, 256), 256, 0, st>>>(c->sp, c->P[a], c->keys, c->arrival, c->cell_count, c->err_dev);
+    k_scan_reduce<<<nb_cells, SCAN_THREADS, 0, st>>>(c->cell_count, c->ncell, c->block_sums);
+    k_scan_spine<<<1, 1024, 0, st>>>(c->block_sums, nb_cells);
+    k_scan_apply<<<nb_cells, SCAN_THREADS, 0, st>>>(c->cell_count, c->ncell, c->block_sums, c->cell_end);
+    k_place<<<nblocks(c->n, 256), 256, 0, st>>>(c->n, c->keys, c->arrival, c->cell_end, c->ids, nullptr, c->rank_key);
+    k_g1_order<<<nblocks(c->n, 256), 256, 0, st>>>(c->n, c->keys, c->ids, c->cell_end, c->keys_sorted);
+    k_g1_neighbors<<<nblocks(c->n, 128), 128, 0, st>>>(c->sp, c->P[a], c->Q[a], c->cell_end, c->keys_sorted,
+                                                       c->nbr, c->nbr_num, c->err_dev);
+    c->launches += 7;
+    CU(cudaGetLastError());
+    c->phase = 1;
+    c->have_sorted = true;
+    return TISPH_OK;
+}
+
 static int run_update(tisph_ctx* c) {
     if (c->phase != 0) return fail(TISPH_ERR_INVALID, "UPDATE issued out of order (phase %d)", c->phase);
+    if (c->cfg.generation == 1) return run_update_gen1(c);
     cudaStream_t st = c->stream;
     c->sp.n = c->n;
     int a = c->cur, b = c->cur ^ 1;
@@ -215,6 +242,14 @@ static int run_density(tisph_ctx* c) {
     if (c->phase != 1) return fail(TISPH_ERR_INVALID, "DENSITY issued out of order (phase %d)", c->phase);
     int b = c->cur;
     cudaStream_t st = c->stream;
+    if (c->cfg.generation == 1) {
+        k_g1_density<<<nblocks(c->n, 128), 128, 0, st>>>(c->sp, c->P[b], c->Q[b], c->nbr, c->nbr_num, c->D, c->S,
+                                                         c->ncount);
+        c->launches += 1;
+        CU(cudaGetLastError());
+        c->phase = 2;
+        return TISPH_OK;
+    }
     auto kd = c->sp.volume_mode == 1 ? k_density_list<true> : k_density_list<false>;
     kd<<<c->grid_dl, NB_THREADS, DL_SMEM, st>>>(
         c->sp, c->cell_end, c->items, c->ctr, c->list_items_cap, c->variant == 1, c->P[b], c->V[b], c->Q[b],
@@ -233,6 +268,15 @@ static int run_force(tisph_ctx* c) {
     cudaStream_t st = c->stream;
     float4* dnp = c->diagnostics ? c->a_np : nullptr;
     float4* dp = c->diagnostics ? c->a_p : nullptr;
+    if (c->cfg.generation == 1) {
+        k_g1_force<<<nblocks(c->n, 128), 128, 0, st>>>(c->sp, c->P[b], c->V[b], c->Q[b], c->D, c->nbr, c->nbr_num,
+                                                       c->P[a], c->V[a], c->Q[a], c->dvel, dnp, dp);
+        c->launches += 1;
+        CU(cudaGetLastError());
+        c->cur = a;
+        c->phase = 0;
+        return TISPH_OK;
+    }
     auto kf = c->has_boundary ? k_force_list<true> : k_force_list<false>;
     kf<<<c->grid_fl, NB_THREADS, FL_SMEM, st>>>(
         c->sp, c->cell_end, c->items, c->ctr, c->P[b], c->V[b], c->Q[b], c->D, c->P[a], c->V[a], c->Q[a],
@@ -264,8 +308,9 @@ int tisph_create(const tisph_config* cfg, tisph_ctx** out) {
     if (cfg->struct_size != (int32_t)sizeof(tisph_config))
         return fail(TISPH_ERR_INVALID, "tisph_config size mismatch: got %d, library has %d",
                     cfg->struct_size, (int)sizeof(tisph_config));
-    if (cfg->generation != 2 || cfg->dim != 3)
-        return fail(TISPH_ERR_INVALID, "only generation 2 / dim 3 is implemented in this build");
+    if (!((cfg->generation == 2 && cfg->dim == 3) || (cfg->generation == 1 && cfg->dim == 2)))
+        return fail(TISPH_ERR_INVALID, "generation 2 is the 3D path, generation 1 the 2D path (got generation %d, dim %d)",
+                    cfg->generation, cfg->dim);
     if (cfg->capacity <= 0 || cfg->support <= 0.f) return fail(TISPH_ERR_INVALID, "bad capacity/support");
     int64_t ncell = (int64_t)cfg->grid_num[0] * cfg->grid_num[1] * (cfg->dim == 3 ? cfg->grid_num[2] : 1);
     if (ncell <= 0 || ncell > 0x7fffffff) return fail(TISPH_ERR_INVALID, "grid too large");
@@ -298,6 +343,11 @@ int tisph_create(const tisph_config* cfg, tisph_ctx** out) {
         c->items_cap = (int)(occupied_max + (int64_t)cap / 32 + 2);
         int64_t budget = (int64_t)cap / 28 + 1024;           // items that get a neighbour list (48 KiB each)
         c->list_items_cap = (int)(budget < c->items_cap ? budget : c->items_cap);
+        if (cfg->generation == 1) { c->items_cap = 1; c->list_items_cap = 1; }   // gen-1 walks an explicit table
+    }
+    if (cfg->generation == 1) {
+        A(dalloc(&c->nbr, cap * G1_MAX_NEIGHBORS));
+        A(dalloc(&c->nbr_num, cap));
     }
     A(dalloc(&c->items, (size_t)c->items_cap));
     A(dalloc(&c->ctr, 1));
@@ -316,6 +366,7 @@ int tisph_create(const tisph_config* cfg, tisph_ctx** out) {
         A(cudaMemsetAsync(c->keys_sorted, 0, cap * 4, c->stream));
         A(cudaMemsetAsync(c->cell_end, 0, (size_t)c->ncell * 4, c->stream));
         A(cudaMemsetAsync(c->cell_count, 0, (size_t)c->ncell * 4, c->stream));
+        if (c->nbr_num) A(cudaMemsetAsync(c->nbr_num, 0, cap * 4, c->stream));
         A(cudaFuncSetAttribute(k_density_list<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DL_SMEM));
         A(cudaFuncSetAttribute(k_density_list<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DL_SMEM));
         A(cudaFuncSetAttribute(k_force_list<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FL_SMEM));
@@ -356,6 +407,7 @@ int tisph_destroy(tisph_ctx* c) {
     cudaFree(c->items); cudaFree(c->ctr); cudaFree(c->fb_d); cudaFree(c->fb_f); cudaFree(c->item_flags);
     cudaFree(c->Lg); cudaFree(c->Lcnt);
     cudaFree(c->rank_key); cudaFree(c->range_dev); cudaFree(c->shard_ctr);
+    cudaFree(c->nbr); cudaFree(c->nbr_num);
     for (int k = 0; k < 4; ++k) cudaFree(c->msg[k]);
     if (c->ev_made)
         for (int s = 0; s < MAX_TIMED_STEPS; ++s)
@@ -516,6 +568,11 @@ static int check_device_errors(tisph_ctx* c) {
         CU(cudaMemsetAsync(c->err_dev, 0, 16, c->stream));
         return fail(TISPH_ERR_DOMAIN, "%d particle(s) left the grid (the reference reads out of bounds here)", err[0]);
     }
+    if (err[1]) {
+        CU(cudaMemsetAsync(c->err_dev, 0, 16, c->stream));
+        return fail(TISPH_ERR_CAPACITY, "%d overflow(s) of the gen-1 cell lists (100 per cell) / neighbour lists (100): "
+                                        "undefined behaviour in the reference", err[1]);
+    }
     return TISPH_OK;
 }
 
@@ -553,9 +610,13 @@ int tisph_download(tisph_ctx* c, int32_t field, void* dst, size_t bytes) {
             if (!c->a_np) return fail(TISPH_ERR_INVALID, "enable TISPH_P_DIAGNOSTICS before the step");
             src = field == TISPH_F_A_NONPRESSURE ? c->a_np : c->a_p; comp0 = 0; ncomp = dim; break;
         case TISPH_F_DENSITY_SUM: direct = c->S; break;
-        case TISPH_F_NEIGHBOR_COUNT: direct = c->ncount; break;
+        case TISPH_F_NEIGHBOR_COUNT: direct = c->cfg.generation == 1 ? c->nbr_num : c->ncount; break;
+        case TISPH_F_NEIGHBORS:
+            if (c->cfg.generation != 1) return fail(TISPH_ERR_INVALID, "gen-2 keeps no explicit neighbour table");
+            direct = c->nbr; count = (size_t)n * G1_MAX_NEIGHBORS; break;
         case TISPH_F_GRID_IDS: direct = c->keys_sorted; break;
-        case TISPH_F_GRID_PARTICLES_NUM: direct = c->cell_end; count = (size_t)c->ncell; break;
+        case TISPH_F_GRID_PARTICLES_NUM:      // gen-2: inclusive scan; gen-1: per-cell counts (partice_system.py:131)
+            direct = c->cfg.generation == 1 ? c->cell_count : c->cell_end; count = (size_t)c->ncell; break;
         case TISPH_F_CELL_COUNT: direct = c->cell_count; count = (size_t)c->ncell; break;
         case TISPH_F_COLOR:
             if (c->sharded) return fail(TISPH_ERR_INVALID, "colour is kept by the host side of a sharded run");

@@ -16,6 +16,7 @@ _FIELD_SPEC = {   # field -> (dtype, components: 'dim' | int | 'color' | 'cell')
     _capi.F_DENSITY_RAW: (np.float32, 1), _capi.F_NEIGHBOR_COUNT: (np.int32, 1),
     _capi.F_ORIG_ID: (np.int32, 1), _capi.F_A_NONPRESSURE: (np.float32, "dim"),
     _capi.F_A_PRESSURE: (np.float32, "dim"), _capi.F_CELL_COUNT: (np.int32, "cell"),
+    _capi.F_NEIGHBORS: (np.int32, 100),
 }
 
 
@@ -100,6 +101,8 @@ class Engine:
             return dtype, (n, self.dim)
         if comp == "color":
             return dtype, ((n, 3) if self.generation == 2 else (n,))
+        if isinstance(comp, int) and comp > 1:
+            return dtype, (n, comp)
         return dtype, (n,)
 
     def download(self, field, out=None):

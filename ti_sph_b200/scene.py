@@ -95,3 +95,45 @@ def gen2_config(configuration, capacity, device=0, density_mode=0, volume_mode=0
     c.eps_h2 = 0.01 * h ** 2
     c.density_mode, c.volume_mode = int(density_mode), int(volume_mode)
     return c
+
+
+DEMO_2D = {               # data/scenes/demo_2d.json of the reference (the keys gen-1 consumes)
+    "configuration": {"domainStart": [0.0, 0.0, 0.0], "domainEnd": [5.0, 3.0, 2.0], "particleRadius": 0.01,
+                      "density0": 1000, "viscosity": 0.01, "gravitation": [0.0, -9.81, 0.0]},
+    "rigidBodies": [],
+    "fluidBlocks": [{"objectId": 1, "start": [3, 1], "end": [6, 6], "velocity": [0, -20], "density": 1000.0,
+                     "color": [50, 100, 200]}],
+}
+
+GEN1_GRAVITY = -9.80      # core/const.py:2
+
+
+def gen1_config(res, device=0):
+    """tisph_config for ParticleSystem / ParticleSystemV2 + WCSPH (2D; partice_system.py:8-34,
+    sph_base.py:10-16, wcsph.py:8-15).  Everything but `res` is hard-coded in the reference."""
+    dim = len(res)
+    if dim != 2:
+        raise ValueError("the gen-1 path is 2D (the reference's 3D variant of it is not runnable)")
+    r = 0.05                                                   # partice_system.py:20
+    h = r * 4.0                                                # :22
+    m_V = 0.8 * (2 * r) ** dim                                 # :23
+    grid_num = np.ceil(np.array(res) / h).astype(int)          # :30 (pixel resolution / support radius)
+    kw, kdw = kernel_constants(dim, h)
+    c = _capi.Config()
+    c.struct_size = _capi.C.sizeof(_capi.Config)
+    c.generation, c.dim, c.device, c.capacity = 1, dim, device, 2 ** 15      # :24
+    c.grid_num[:] = [int(grid_num[0]), int(grid_num[1]), 1]
+    c.support = h
+    c.padding = h                                              # :34
+    c.m_V0 = m_V
+    c.dt = 2e-4                                                # sph_base.py:14-15
+    c.gravity[:] = [0.0, GEN1_GRAVITY, 0.0]                    # wcsph.py:59: d_v[dim-1] = const.g
+    c.rho0 = 1000.0                                            # sph_base.py:13
+    c.ps_density0 = 1000.0
+    c.stiffness, c.exponent = 50.0, 7.0                        # wcsph.py:10-11
+    c.k_w, c.k_dw = kw, kdw
+    c.eps_h2 = 0.01 * h ** 2                                   # sph_base.py:82
+    c.g1_visc_c = 2 * (dim + 2) * 0.05                         # sph_base.py:81
+    c.g1_mass = m_V * 1000.0                                   # sph_base.py:16
+    c.g1_press_c = -1000.0 * m_V                               # sph_base.py:68
+    return c
