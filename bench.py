@@ -102,15 +102,33 @@ class ClockSampler:
         return out
 
 
-def workload_scene(name):
+def workload_scene(name, with_mesh=True):
+    """BASELINE.md configurations.  C4 adds a mesh-sampled boundary: data/models/Dragon_50k.obj when
+    the user has put it there (it is the reference's asset and is not copied into this repo),
+    otherwise a procedural 50,000-triangle torus of similar size."""
     from ti_sph_b200 import scene as sc
-    return sc.bench_scene(name)
+    s = sc.bench_scene(name)
+    if name == "C4" and with_mesh:
+        from ti_sph_b200 import mesh
+        path = os.path.join(ROOT, "data", "models", "Dragon_50k.obj")
+        body = {"scale": [1, 1, 1], "rotationAngle": 0, "rotationAxis": [0, 1, 0], "color": [255, 255, 255],
+                "velocity": [0.0, 0.0, 0.0], "density": 1000.0}
+        if os.path.exists(path):
+            v, _ = mesh.load_obj(path)
+            body.update(geometryFile=path, translation=list(np.array([1.0, 0.06, 0.75]) - [v[:, 0].mean(), v[:, 1].min(), v[:, 2].mean()]))
+        else:
+            path = os.path.join(tempfile.gettempdir(), "tisph_c4_torus_50k.obj")
+            if not os.path.exists(path):
+                mesh.write_obj(path, *mesh.torus(0.45, 0.12, (0.0, 0.0, 0.0), nu=250, nv=100))
+            body.update(geometryFile=path, translation=[1.0, 0.25, 0.75])
+        s["rigidBodies"] = [body]
+    return s
 
 
 def sample_scene(name, target_particles):
     """A bounded sample of workload `name` for the CPU legs: same radius/grid/velocity, the
     fluid block cut down along x then y to ~target_particles."""
-    s = workload_scene(name)
+    s = workload_scene(name, with_mesh=False)           # the CPU legs time a cut of the fluid block only
     blk = s["fluidBlocks"][0]
     r = s["configuration"]["particleRadius"]
     dims = [int(round((blk["end"][i] - blk["start"][i]) / r)) for i in range(3)]

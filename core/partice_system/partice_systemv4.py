@@ -98,9 +98,12 @@ class ParticleSystemV4:
             rigid['partice_num'] = num
             rigid['voxelized_points'] = points
             density = rigid.get('density')
-            # the reference hands a float (num,3) colour array to an i32 3-vector field;
-            # integer RGB is stored here
-            color = np.tile(np.array(rigid.get('color', [0, 0, 0]), dtype=np.int32), (num, 1))
+            # the reference divides integer RGB by 255.0 and hands the float (num,3) array to the
+            # i32 colour field (:111-114,190), which truncates: [255,255,255] is stored as (1,1,1)
+            color = rigid.get('color', [0, 0, 0])
+            if type(color[0]) == int:
+                color = [c / 255.0 for c in color]
+            color = np.tile(np.array(color, dtype=np.float32).astype(np.int32), (num, 1))
             self.add_particles(num, points,
                                np.tile(np.array(rigid['velocity'], dtype=np.float32), (num, 1)),
                                np.full(num, density if density is not None else 1000.0),

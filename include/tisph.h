@@ -197,6 +197,16 @@ int tisph_shard_buffer(tisph_ctx *ctx, int32_t which, void **ptr, int32_t *capac
 /* Make the received records part of the particle set of the coming step. */
 int tisph_shard_append(tisph_ctx *ctx, int32_t n_from_left, int32_t n_from_right);
 
+/* ---- mesh -> boundary particles: the sampling step of ParticleSystemV4.load_rigid_body
+ * (partice_systemv4.py:276-277: mesh.voxelized(pitch=particle_diameter).fill().points, trimesh).
+ * vertices [nv][3] f32 (already scaled / rotated / translated), faces [nf][3] i32.  Voxel centres
+ * lie on the world lattice k * pitch; the grid covers lattice indices lo[k] .. lo[k]+dims[k]-1 and
+ * must leave one empty layer around the mesh.  occupancy [dims0][dims1][dims2] u8 (host) receives 1
+ * for surface voxels and, if `fill`, for every voxel not connected to the outside. */
+int tisph_voxelize_mesh(int32_t device, const float *vertices, int32_t nv, const int32_t *faces,
+                        int32_t nf, float pitch, int32_t fill, const int32_t *lo, const int32_t *dims,
+                        uint8_t *occupancy);
+
 #ifdef __cplusplus
 }
 #endif

@@ -14,6 +14,7 @@
 #include "tisph_walk.cuh"
 #include "tisph_shard.cuh"
 #include "tisph_gen1.cuh"
+#include "tisph_voxel.cuh"
 
 using namespace tisph;
 
@@ -848,6 +849,55 @@ int tisph_shard_append(tisph_ctx* c, int32_t n_from_left, int32_t n_from_right) 
     c->sp.n = c->n;
     c->appended = true;
     c->have_sorted = false;
+    return TISPH_OK;
+}
+
+// ------------------------------------------------------------------ mesh sampler (8(f) rank 1)
+int tisph_voxelize_mesh(int32_t device, const float* vertices, int32_t nv, const int32_t* faces, int32_t nf,
+                        float pitch, int32_t fill, const int32_t* lo, const int32_t* dims,
+                        uint8_t* occupancy) {
+    if (!vertices || !faces || !lo || !dims || !occupancy || nv <= 0 || nf <= 0 || pitch <= 0.f)
+        return fail(TISPH_ERR_INVALID, "bad argument");
+    if (tisph_device_count() <= 0)
+        return fail(TISPH_ERR_NO_DEVICE, "no CUDA device visible; libtisph has no CPU fallback");
+    for (int32_t f = 0; f < 3 * nf; ++f)
+        if (faces[f] < 0 || faces[f] >= nv) return fail(TISPH_ERR_INVALID, "face index %d out of range", faces[f]);
+    CU(cudaSetDevice(device));
+    VoxGrid g;
+    size_t total = 1;
+    for (int k = 0; k < 3; ++k) {
+        if (dims[k] < 3) return fail(TISPH_ERR_INVALID, "grid needs an empty padding layer on every side");
+        g.lo[k] = lo[k]; g.dims[k] = dims[k];
+        total *= (size_t)dims[k];
+    }
+    if (total > ((size_t)1 << 33)) return fail(TISPH_ERR_CAPACITY, "voxel grid of %zu cells is too large", total);
+    g.pitch = pitch;
+    float* d_v = nullptr; int* d_f = nullptr; unsigned char *d_occ = nullptr, *d_out = nullptr; int* d_chg = nullptr;
+    cudaError_t e = cudaSuccess;
+    auto A = [&](cudaError_t r) { if (e == cudaSuccess) e = r; };
+    A(cudaMalloc(&d_v, (size_t)nv * 12)); A(cudaMalloc(&d_f, (size_t)nf * 12));
+    A(cudaMalloc(&d_occ, total)); A(cudaMalloc(&d_out, total)); A(cudaMalloc(&d_chg, 4));
+    if (e == cudaSuccess) {
+        A(cudaMemcpy(d_v, vertices, (size_t)nv * 12, cudaMemcpyHostToDevice));
+        A(cudaMemcpy(d_f, faces, (size_t)nf * 12, cudaMemcpyHostToDevice));
+        A(cudaMemset(d_occ, 0, total)); A(cudaMemset(d_out, 0, total));
+        k_vox_surface<<<nblocks(nf, 128), 128>>>(g, d_v, d_f, nf, d_occ);
+        if (fill) {
+            int ncol = dims[0] * dims[1];
+            for (int it = 0; it < 4096 && e == cudaSuccess; ++it) {
+                int chg = 0;
+                A(cudaMemset(d_chg, 0, 4));
+                k_vox_flood<<<nblocks(ncol, 128), 128>>>(g, d_occ, d_out, d_chg);
+                A(cudaMemcpy(&chg, d_chg, 4, cudaMemcpyDeviceToHost));
+                if (!chg) break;
+            }
+            k_vox_fill<<<(unsigned)((total + 255) / 256), 256>>>(total, d_occ, d_out);
+        }
+        A(cudaGetLastError());
+        A(cudaMemcpy(occupancy, d_occ, total, cudaMemcpyDeviceToHost));
+    }
+    cudaFree(d_v); cudaFree(d_f); cudaFree(d_occ); cudaFree(d_out); cudaFree(d_chg);
+    if (e != cudaSuccess) return fail(TISPH_ERR_CUDA, "voxelisation failed: %s", cudaGetErrorString(e));
     return TISPH_OK;
 }
 
