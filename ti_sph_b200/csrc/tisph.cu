@@ -65,11 +65,12 @@ struct tisph_ctx {
     // work items of the neighbour walks + neighbour lists handed from walk 1 to walk 2
     int2* items = nullptr;
     int items_cap = 0, list_items_cap = 0;
+    int pool_rows_cap = 0;
+    int* item_row = nullptr;
     StepCounters* ctr = nullptr;
     int *fb_d = nullptr, *fb_f = nullptr;
     unsigned char* item_flags = nullptr;
     uint2* Lg = nullptr;
-    unsigned short* Lcnt = nullptr;
     int grid_dl = 0, grid_fl = 0, grid_dfb = 0, grid_ffb = 0;   // persistent grids (SMs x resident CTAs)
     void* staging = nullptr;
     size_t staging_bytes = 0;
@@ -253,8 +254,8 @@ static int run_density(tisph_ctx* c) {
     }
     auto kd = c->sp.volume_mode == 1 ? k_density_list<true> : k_density_list<false>;
     kd<<<c->grid_dl, NB_THREADS, DL_SMEM, st>>>(
-        c->sp, c->cell_end, c->items, c->ctr, c->list_items_cap, c->variant == 1, c->P[b], c->V[b], c->Q[b],
-        c->D, c->S, c->ncount, c->Lg, c->Lcnt, c->item_flags, c->fb_d, c->fb_f);
+        c->sp, c->cell_end, c->items, c->ctr, c->pool_rows_cap, c->variant == 1, c->P[b], c->V[b], c->Q[b],
+        c->D, c->S, c->ncount, c->Lg, c->item_row, c->item_flags, c->fb_d, c->fb_f);
     k_density_fb<<<c->grid_dfb, NB_THREADS, DF_SMEM, st>>>(c->sp, c->cell_end, c->items, c->ctr, c->fb_d,
                                                           c->P[b], c->V[b], c->Q[b], c->D, c->S, c->ncount);
     c->launches += 2;
@@ -281,7 +282,7 @@ static int run_force(tisph_ctx* c) {
     auto kf = c->has_boundary ? k_force_list<true> : k_force_list<false>;
     kf<<<c->grid_fl, NB_THREADS, FL_SMEM, st>>>(
         c->sp, c->cell_end, c->items, c->ctr, c->P[b], c->V[b], c->Q[b], c->D, c->P[a], c->V[a], c->Q[a],
-        c->dvel, dnp, dp, c->Lg, c->Lcnt, c->item_flags);
+        c->dvel, dnp, dp, c->Lg, c->item_row, c->item_flags);
     k_force_fb<<<c->grid_ffb, NB_THREADS, FF_SMEM, st>>>(
         c->sp, c->cell_end, c->items, c->ctr, c->fb_f, c->P[b], c->V[b], c->Q[b], c->D, c->P[a], c->V[a],
         c->Q[a], c->dvel, dnp, dp);
@@ -354,8 +355,9 @@ int tisph_create(const tisph_config* cfg, tisph_ctx** out) {
     A(dalloc(&c->ctr, 1));
     A(dalloc(&c->fb_d, (size_t)c->items_cap)); A(dalloc(&c->fb_f, (size_t)c->items_cap));
     A(dalloc(&c->item_flags, (size_t)c->items_cap));
-    A(dalloc(&c->Lg, (size_t)c->list_items_cap * ITEM_LIST_WORDS));
-    A(dalloc(&c->Lcnt, (size_t)c->list_items_cap * NB_THREADS));
+    c->pool_rows_cap = c->list_items_cap * POOL_ROWS_PER_FULL_ITEM;        // neighbour-list pool, ~1.75 KB per particle
+    A(dalloc(&c->Lg, (size_t)c->pool_rows_cap * NB_THREADS));
+    A(dalloc(&c->item_row, (size_t)c->items_cap));
     c->staging_bytes = cap * 16 * 3;
     A(cudaMalloc(&c->staging, c->staging_bytes));
     if (e == cudaSuccess) {
@@ -406,7 +408,7 @@ int tisph_destroy(tisph_ctx* c) {
     cudaFree(c->snapP); cudaFree(c->snapV); cudaFree(c->snapQ);
     cudaFree(c->block_sums); cudaFree(c->color); cudaFree(c->err_dev); cudaFree(c->staging);
     cudaFree(c->items); cudaFree(c->ctr); cudaFree(c->fb_d); cudaFree(c->fb_f); cudaFree(c->item_flags);
-    cudaFree(c->Lg); cudaFree(c->Lcnt);
+    cudaFree(c->Lg); cudaFree(c->item_row);
     cudaFree(c->rank_key); cudaFree(c->range_dev); cudaFree(c->shard_ctr);
     cudaFree(c->nbr); cudaFree(c->nbr_num);
     for (int k = 0; k < 4; ++k) cudaFree(c->msg[k]);

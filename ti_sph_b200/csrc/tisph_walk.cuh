@@ -32,14 +32,17 @@ constexpr int CHUNK = 32;              // candidates filtered between drain chec
 constexpr float FAR = 1e18f;           // padding candidates / idle targets: never within the cutoff
 constexpr int TCAP = 1792;             // candidates of one shared-memory tile (27 cells x 64 at the reference spacing = 1728)
 constexpr int KCAP = 96;               // neighbour-list entries per thread and item in global memory
-constexpr int ITEM_LIST_WORDS = NB_THREADS * KCAP / 4;   // uint2 words of one item's lists
+// Neighbour-list pool: an item reserves 1 + need rows of NB_THREADS uint2 words -- row 0 holds the
+// per-thread word counts, then `need` <= KCAP/4 rows of list words ([word][thread]).  `need` is
+// bounded by the tile size, so sparse cells take a few hundred bytes and dense ones 48 KiB.
+constexpr int POOL_ROWS_PER_FULL_ITEM = KCAP / 4 + 1;
 
 struct StepCounters {
     int n_items;        // built by k_items
     int work_d, work_f; // work-stealing cursors of the list kernels
     int n_fb_d, n_fb_f; // items handed to the fallback kernels
     int work_fb_d, work_fb_f;
-    int pad;
+    int pool_rows;      // bump allocator of the neighbour-list pool (rows of NB_THREADS 8-byte words)
 };
 
 // number of candidates in the 27-cell neighbourhood of cell c (9 contiguous ranges, see above)
@@ -292,10 +295,10 @@ __device__ __forceinline__ void filter8(uint32_t a0, uint32_t o0, float2 xi2, fl
 template <bool AKINCI>
 __global__ void __launch_bounds__(NB_THREADS, 3)
 k_density_list(SimParams sp, const int* __restrict__ cell_end, const int2* __restrict__ items,
-               StepCounters* __restrict__ ctr, int list_items_cap, int all_to_fallback,
+               StepCounters* __restrict__ ctr, int pool_rows_cap, int all_to_fallback,
                const float4* __restrict__ P, float4* __restrict__ V, const float4* __restrict__ Q,
                float4* __restrict__ D, float* __restrict__ S, int* __restrict__ ncount,
-               uint2* __restrict__ Lg, unsigned short* __restrict__ Lcnt, unsigned char* __restrict__ flags,
+               uint2* __restrict__ Lg, int* __restrict__ item_row, unsigned char* __restrict__ flags,
                int* __restrict__ fb_d, int* __restrict__ fb_f) {
     extern __shared__ float4 dyn_smem[];
     float4* T = dyn_smem;                                                   // [TCAP/2 + 1][2]
@@ -304,7 +307,7 @@ k_density_list(SimParams sp, const int* __restrict__ cell_end, const int2* __res
     __shared__ float red_w[NB_THREADS];
     __shared__ float red_b[NB_THREADS];
     __shared__ int red_c[NB_THREADS];
-    __shared__ int s_slot, s_over;
+    __shared__ int s_slot, s_over, s_row;
 
     const int tid = threadIdx.x;
     const float cut_wide = sp.d2_cut * 1.000001f;       // superset filter; the drain applies the exact test
@@ -327,8 +330,22 @@ k_density_list(SimParams sp, const int* __restrict__ cell_end, const int2* __res
             continue;
         }
         const bool own = G.c >= sp.own_key_lo && G.c < sp.own_key_hi;   // ghost cells get no force walk
-        const bool keep_list = own && it < list_items_cap;
-        if (tid == 0) s_over = keep_list ? 0 : 1;
+        // rows of list words this item can need: every candidate of my share accepted, + padding per tile
+        const int ntile = (G.total + TCAP - 1) / TCAP;
+        const int share = (G.total + 2 * G.nsplit - 1) / (2 * G.nsplit) * 2;       // candidates one thread filters
+        // ~15 % of them are neighbours (sphere / 27 cells); reserve for 60 % -- a list that still overflows
+        // sends the item to the fallback force kernel
+        const int need = min(KCAP / 4, (share * 3 / 5 + 3) / 4 + 2 * ntile + 1);
+        if (tid == 0) {
+            int row = -1;
+            if (own) {
+                row = atomicAdd(&ctr->pool_rows, need + 1);
+                if (row + need + 1 > pool_rows_cap) row = -1;     // pool exhausted: this item takes the fallback force kernel
+            }
+            s_row = row;
+            s_over = row < 0 ? 1 : 0;
+            item_row[it] = row;
+        }
         const int t_local = tid % G.tl, split = tid / G.tl;
         const int i = G.i0 + t_local;
         const bool active = t_local < G.nT;
@@ -338,7 +355,6 @@ k_density_list(SimParams sp, const int* __restrict__ cell_end, const int2* __res
         const float2 xi2 = make_float2(pi.x, pi.x), yi2 = make_float2(pi.y, pi.y), zi2 = make_float2(pi.z, pi.z);
         float wsum = 0.f, wbsum = 0.f;
         int cnt = 0, pend = 0, gword = 0;          // gword: 4-entry words already written to the global list
-        uint2* gl = Lg + (size_t)it * ITEM_LIST_WORDS + tid;
         // the candidates are walked tile by tile (one tile at the reference spacing)
         for (int tile0 = 0; tile0 < G.total; tile0 += TCAP) {
             const int tile_n = min(TCAP, G.total - tile0);
@@ -366,6 +382,8 @@ k_density_list(SimParams sp, const int* __restrict__ cell_end, const int2* __res
             }
             __syncthreads();
             // ---- walk -----------------------------------------------------------------------
+            const bool keep_list = s_row >= 0;                    // (written by thread 0 before the barrier)
+            uint2* gl = Lg + (size_t)(keep_list ? s_row + 1 : 0) * NB_THREADS + tid;
             const int self_r = self_t - tile0;
             const uint32_t self_o = (self_r >= 0 && self_r < TCAP)
                                         ? (uint32_t)(8 * pair_slot(self_r >> 1, G.nsplit) + (self_r & 1)) : 0xffffffffu;
@@ -383,7 +401,7 @@ k_density_list(SimParams sp, const int* __restrict__ cell_end, const int2* __res
                     const int lim = last ? pend : nd;                     // entries that are mine to evaluate now
                     const int nd_max = __reduce_max_sync(0xffffffffu, nd);
                     uint2* gp = gl + (size_t)gword * NB_THREADS;
-                    const int groom = keep_list ? KCAP / 4 - gword : 0;   // words that still fit the global list
+                    const int groom = keep_list ? need - gword : 0;       // words that still fit the item's list rows
                     for (int k4 = 0; k4 < nd_max; k4 += 4, gp += NB_THREADS) {
                         uint32_t ew[4];
 #pragma unroll
@@ -413,9 +431,11 @@ k_density_list(SimParams sp, const int* __restrict__ cell_end, const int2* __res
             }
             // every split drains completely at the end of a tile: pend == 0 at every tile boundary
         }
+        if (G.total <= 0) __syncthreads();                 // no tile was staged: publish s_row (uniform branch)
+        const bool keep_list = s_row >= 0;
         if (keep_list) {
-            Lcnt[(size_t)it * NB_THREADS + tid] = (unsigned short)min(gword, KCAP / 4);     // in words
-            if (gword > KCAP / 4) s_over = 1;              // benign race: every writer stores 1
+            Lg[(size_t)s_row * NB_THREADS + tid] = make_uint2((unsigned)min(gword, need), 0u);   // count row, in words
+            if (gword > need) s_over = 1;                  // benign race: every writer stores 1
         }
         red_w[tid] = wsum;
         red_b[tid] = wbsum;
@@ -512,7 +532,7 @@ k_force_list(SimParams sp, const int* __restrict__ cell_end, const int2* __restr
              const float4* __restrict__ D, float4* __restrict__ Pout, float4* __restrict__ Vout,
              float4* __restrict__ Qout, float4* __restrict__ dvel, float4* __restrict__ a_np_out,
              float4* __restrict__ a_p_out, const uint2* __restrict__ Lg,
-             const unsigned short* __restrict__ Lcnt, const unsigned char* __restrict__ flags) {
+             const int* __restrict__ item_row, const unsigned char* __restrict__ flags) {
     extern __shared__ float4 dyn_smem[];
     float4* tP = dyn_smem;
     float4* tV = dyn_smem + FTILE;
@@ -549,8 +569,9 @@ k_force_list(SimParams sp, const int* __restrict__ cell_end, const int2* __restr
         const float rho_i = di.x, pr_i = di.y;
         const float nub_i = sp.visc_bound_c / (2.0f * rho_i);     // wcsphv2.py:76
         ForceAcc A = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        const int nw = walker ? (int)Lcnt[(size_t)it * NB_THREADS + tid] : 0;     // words of 4 entries
-        const uint2* gl = Lg + (size_t)it * ITEM_LIST_WORDS + tid;
+        const uint2* gl = Lg + (size_t)item_row[it] * NB_THREADS + tid;
+        const int nw = walker ? (int)gl[0].x : 0;                 // words of 4 entries (count row)
+        gl += NB_THREADS;
         uint2 w = nw > 0 ? gl[0] : make_uint2(0u, 0u);
         if (G.total <= TCAP) {
             // ---- one tile (the common case): replay the whole list
