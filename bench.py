@@ -385,7 +385,7 @@ def main():
     ap.add_argument("--mode", default="reference", choices=["reference", "summed"],
                     help="density mode: reference = bit-faithful to wcsphv2.py:32-34, summed = intent")
     ap.add_argument("--e2e-steps", type=int, default=5)
-    ap.add_argument("--pre-steps", type=int, default=50, help="steps from the lattice before the state is saved")
+    ap.add_argument("--pre-steps", type=int, default=10, help="steps from the lattice before the state is saved")
     ap.add_argument("--chain", type=int, default=5, help="steps per replay chain (main_3d.py renders every 5)")
     ap.add_argument("--cpu-particles", type=int, default=500000, help="size of the cpu_baseline sample")
     ap.add_argument("--ref-particles", type=int, default=250000, help="sample size of --impl reference")

@@ -186,9 +186,12 @@ int tisph_stage_times(tisph_ctx *ctx, int32_t enable, float *ms_update, float *m
  * After tisph_shard_config every per-particle accessor (tisph_particle_num, tisph_download,
  * tisph_device_ptr, tisph_state_save/restore) covers the OWNED particles only. */
 /* ghost_planes: 1 when a particle's density needs no neighbour data (density_mode 0 with
- * volume_mode 0), else 2.  message_capacity: records per message buffer. */
+ * volume_mode 0), else 2.  left_lo / right_hi: the far edges of the neighbouring slabs
+ * [left_lo, plane_lo) and [plane_hi, right_hi), -1 where there is no neighbour; a particle may
+ * migrate anywhere into a neighbouring slab within one step.  message_capacity: records per
+ * message buffer. */
 int tisph_shard_config(tisph_ctx *ctx, int32_t plane_lo, int32_t plane_hi, int32_t ghost_planes,
-                       int32_t has_left, int32_t has_right, int32_t message_capacity);
+                       int32_t left_lo, int32_t right_hi, int32_t message_capacity);
 /* Fill the two send buffers from the owned particles: every particle within ghost_planes of a
  * slab face, or beyond it (a migrant), goes to that neighbour.  Synchronous; returns counts. */
 int tisph_shard_pack(tisph_ctx *ctx, int32_t *n_left, int32_t *n_right);

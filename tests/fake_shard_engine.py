@@ -32,9 +32,9 @@ class FakeShardEngine:
         self.steps = 0
 
     # ---- Engine surface used by ShardedSim
-    def shard_config(self, plane_lo, plane_hi, ghost, has_left, has_right, cap):
+    def shard_config(self, plane_lo, plane_hi, ghost, left_lo, right_hi, cap):
         self.plane_lo, self.plane_hi, self.ghost = plane_lo, plane_hi, ghost
-        self.has_left, self.has_right, self.cap = has_left, has_right, cap
+        self.has_left, self.has_right, self.cap = left_lo >= 0, right_hi >= 0, cap
 
     def set_param(self, param, value):
         if param == K.P_ID_BASE:

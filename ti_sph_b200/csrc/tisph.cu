@@ -83,7 +83,7 @@ struct tisph_ctx {
     // slab sharding (tisph_shard.cuh)
     int *rank_key = nullptr;
     bool sharded = false;
-    int plane_lo = 0, plane_hi = 0, ghost = 1, has_left = 0, has_right = 0;
+    int plane_lo = 0, plane_hi = 0, ghost = 1, left_lo = -1, right_hi = -1;   // neighbours' far edges, -1 = no neighbour
     int in_off = 0;                    // first record of the input slice inside P/V/Q[cur]
     bool appended = false;             // between tisph_shard_append and the step
     int o_lo = 0, o_hi = 0;            // owned slice of the sorted arrays (host copy)
@@ -762,16 +762,16 @@ int tisph_stage_times(tisph_ctx* c, int32_t enable, float* ms_update, float* ms_
 
 // ------------------------------------------------------------------ slab sharding (8(e))
 int tisph_shard_config(tisph_ctx* c, int32_t plane_lo, int32_t plane_hi, int32_t ghost_planes,
-                       int32_t has_left, int32_t has_right, int32_t message_capacity) {
+                       int32_t left_lo, int32_t right_hi, int32_t message_capacity) {
     CHECK_CTX(c);
     if (c->have_sorted || c->appended) return fail(TISPH_ERR_INVALID, "configure the slab before the first step");
     if (plane_lo < 0 || plane_hi > c->sp.gx || plane_lo >= plane_hi || ghost_planes < 1 || ghost_planes > 2 ||
-        message_capacity <= 0)
+        message_capacity <= 0 || left_lo >= plane_lo || (right_hi >= 0 && right_hi <= plane_hi))
         return fail(TISPH_ERR_INVALID, "bad slab [%d,%d) / ghost %d / capacity %d", plane_lo, plane_hi,
                     ghost_planes, message_capacity);
     c->sharded = true;
     c->plane_lo = plane_lo; c->plane_hi = plane_hi; c->ghost = ghost_planes;
-    c->has_left = has_left != 0; c->has_right = has_right != 0;
+    c->left_lo = left_lo < 0 ? -1 : left_lo; c->right_hi = right_hi < 0 ? -1 : right_hi;
     const int plane = c->sp.gy * c->sp.gz;
     c->sp.own_key_lo = plane_lo * plane;
     c->sp.own_key_hi = plane_hi * plane;
@@ -796,7 +796,7 @@ int tisph_shard_pack(tisph_ctx* c, int32_t* n_left, int32_t* n_right) {
     const int n_upper = c->range_valid ? c->o_hi - c->o_lo : c->n;
     if (n_upper > 0) {
         k_shard_pack<<<nblocks(n_upper, 256), 256, 0, st>>>(
-            c->sp, n_upper, c->range_dev, c->plane_lo, c->plane_hi, c->ghost, c->has_left, c->has_right,
+            c->sp, n_upper, c->range_dev, c->plane_lo, c->plane_hi, c->ghost, c->left_lo, c->right_hi,
             c->msg_cap, c->P[c->cur], c->V[c->cur], c->Q[c->cur], c->msg[0], c->msg[1], c->shard_ctr);
         c->launches += 1;
         CU(cudaGetLastError());
@@ -811,8 +811,7 @@ int tisph_shard_pack(tisph_ctx* c, int32_t* n_left, int32_t* n_right) {
         return fail(TISPH_ERR_CAPACITY, "halo message buffers too small: %d record(s) dropped (capacity %d)",
                     h.k.overflow, c->msg_cap);
     if (h.k.lost)
-        return fail(TISPH_ERR_DOMAIN, "%d particle(s) crossed more than %d cell plane(s) beyond the slab in one step",
-                    h.k.lost, c->ghost);
+        return fail(TISPH_ERR_DOMAIN, "%d particle(s) jumped over a whole neighbouring slab in one step", h.k.lost);
     *n_left = h.k.n_left;
     *n_right = h.k.n_right;
     return TISPH_OK;

@@ -19,7 +19,7 @@ constexpr int SHARD_REC_F4 = 3;     // one record = {P, V, Q} = 48 bytes
 struct ShardCounters {
     int n_left, n_right;    // records packed for the left / right neighbour
     int overflow;           // records that did not fit the message buffers
-    int lost;               // particles that moved more than `ghost` planes beyond the slab in one step
+    int lost;               // particles that jumped over the whole neighbouring slab in one step
 };
 
 // sorted-index range of the particles this rank owns: written after every sort
@@ -35,13 +35,14 @@ __global__ void k_owned_range(const int* __restrict__ cell_end, int ncell, int o
 // that no host round trip is needed between the step and the pack).
 __global__ void __launch_bounds__(256)
 k_shard_pack(SimParams sp, int n_upper, const int* __restrict__ range, int plane_lo, int plane_hi,
-             int ghost, int has_left, int has_right, int cap_records,
+             int ghost, int left_lo, int right_hi, int cap_records,
              const float4* __restrict__ P, const float4* __restrict__ V, const float4* __restrict__ Q,
              float4* __restrict__ send_left, float4* __restrict__ send_right,
              ShardCounters* __restrict__ ctr) {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     int first = range[0], end = range[1];
     int i = first + t;
+    const bool has_left = left_lo >= 0, has_right = right_hi >= 0;
     bool valid = t < n_upper && i < end;
     bool to_left = false, to_right = false;
     float4 p, v, q;
@@ -50,7 +51,9 @@ k_shard_pack(SimParams sp, int n_upper, const int* __restrict__ range, int plane
         int cx = cell_coord(p.x, sp.h);
         to_left = has_left && cx < plane_lo + ghost;
         to_right = has_right && cx >= plane_hi - ghost;
-        if ((has_left && cx < plane_lo - ghost) || (has_right && cx >= plane_hi + ghost)) atomicAdd(&ctr->lost, 1);
+        // a migrant may land anywhere inside the neighbour's slab [left_lo, plane_lo) / [plane_hi, right_hi);
+        // beyond it the neighbour would not own it either
+        if ((has_left && cx < left_lo) || (has_right && cx >= right_hi)) atomicAdd(&ctr->lost, 1);
         if (to_left || to_right) { v = V[i]; q = Q[i]; }
     }
     // warp-aggregated slot reservation

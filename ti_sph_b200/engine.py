@@ -143,9 +143,10 @@ class Engine:
         return {"update_ms": a.value, "density_ms": b.value, "force_ms": c.value, "steps": s.value}
 
     # -- slab sharding (include/tisph.h, "spatial-slab sharding") ------------------------------
-    def shard_config(self, plane_lo, plane_hi, ghost_planes, has_left, has_right, message_capacity):
+    def shard_config(self, plane_lo, plane_hi, ghost_planes, left_lo, right_hi, message_capacity):
+        """left_lo / right_hi: far edges of the neighbouring slabs, -1 where there is no neighbour"""
         check(self._lib.tisph_shard_config(self._ctx, int(plane_lo), int(plane_hi), int(ghost_planes),
-                                           int(bool(has_left)), int(bool(has_right)), int(message_capacity)))
+                                           int(left_lo), int(right_hi), int(message_capacity)))
         self._msg_cap = int(message_capacity)
 
     def shard_pack(self):

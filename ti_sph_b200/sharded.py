@@ -214,8 +214,9 @@ class ShardedSim:
             from .engine import Engine
             engine_factory = Engine
         self.engine = eng = engine_factory(cfg)
-        eng.shard_config(self.plane_lo, self.plane_hi, self.ghost, self.has_left, self.has_right,
-                         message_capacity)
+        eng.shard_config(self.plane_lo, self.plane_hi, self.ghost,
+                         self.edges[rank - 1] if self.has_left else -1,
+                         self.edges[rank + 2] if self.has_right else -1, message_capacity)
         if scene["rigidBodies"]:
             eng.set_param(K.P_HAS_BOUNDARY, 1)
         for id0, pos, vel, dens, mat in chunks:
