@@ -55,7 +55,7 @@ def measured_peaks():
 
 class ClockSampler:
     """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -70,7 +70,14 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def mark(self):
+        """start of the timed region: samples taken before it (launched early because nvidia-smi
+        needs ~100 ms to start) are dropped, unless nothing else is left"""
+        import datetime
+        self.t0 = datetime.datetime.now()
+
     def stop(self):
+        import datetime
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
         if self.proc is None:
             return out
@@ -79,26 +86,31 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
+        rows = []
         try:
             for line in open(self.path):
                 f = [x.strip() for x in line.split(",")]
                 if len(f) < 9:
                     continue
                 try:
-                    sm.append(float(f[1])); mx.append(float(f[2]))
+                    ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f")
+                    rows.append((ts, float(f[1]), float(f[2]), f[5:9]))
                 except ValueError:
                     continue
-                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
-                                      "sw_power_cap"), f[5:9]):
-                    if val.lower().startswith("active"):
-                        reasons.add(name)
             os.unlink(self.path)
         except Exception:
             pass
-        if sm:
-            out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)),
-                   "reasons": sorted(reasons), "samples": len(sm)}
+        t0 = getattr(self, "t0", None)
+        timed = [r for r in rows if t0 is None or r[0] >= t0]
+        use = timed or rows[-3:]
+        if use:
+            reasons = set()
+            for r in use:
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            out = {"sm_mhz": float(np.median([r[1] for r in use])), "sm_max_mhz": float(max(r[2] for r in use)),
+                   "reasons": sorted(reasons), "samples": len(use), "samples_in_timed_region": len(timed)}
         return out
 
 
@@ -254,13 +266,14 @@ def run_gpu(args):
         eng.save_state()
     else:
         sim.save_state()
+    clocks = ClockSampler(local_rank)
     run_steps(args.warmup)
     barrier()
     eng.stage_times(True)
     l0 = eng.launch_count
-    clocks = ClockSampler(local_rank)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    clocks.mark()
     ev0.record()
     run_steps(args.steps)
     ev1.record()

@@ -132,6 +132,7 @@ static void fill_params(tisph_ctx* c) {
     s.int_exponent = (e >= 1.0f && e <= 64.0f && e == floorf(e)) ? (int)e : 0;
     s.own_key_lo = 0; s.own_key_hi = 0x7fffffff;
     s.walk_key_lo = 0; s.walk_key_hi = 0x7fffffff;
+    s.ghost_walk = 1;
 }
 
 template <typename T>
@@ -252,6 +253,8 @@ static int run_density(tisph_ctx* c) {
         c->phase = 2;
         return TISPH_OK;
     }
+    // ghost cells: their density is needed by the force walk, but in the reference modes it is mass * W(0)
+    c->sp.ghost_walk = (c->sp.density_mode == 0 && c->sp.volume_mode == 0) ? 0 : 1;
     auto kd = c->sp.volume_mode == 1 ? k_density_list<true> : k_density_list<false>;
     kd<<<c->grid_dl, NB_THREADS, DL_SMEM, st>>>(
         c->sp, c->cell_end, c->items, c->ctr, c->pool_rows_cap, c->variant == 1, c->P[b], c->V[b], c->Q[b],

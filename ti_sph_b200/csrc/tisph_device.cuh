@@ -32,6 +32,7 @@ struct SimParams {
     // slab sharding (tisph_shard.cuh): cell-key ranges [lo, hi).  Unsharded: [0, INT_MAX).
     int own_key_lo, own_key_hi;     // cells whose particles this rank advances
     int walk_key_lo, walk_key_hi;   // cells that get work items (own planes + one ghost plane each side)
+    int ghost_walk;                 // 0: ghost cells need no density walk (rho = mass W(0), no boundary volumes)
 };
 
 // cell = (int)(x / grid_size): IEEE f32 division then truncation (partice_systemv4.py:86-92)

@@ -355,9 +355,11 @@ k_density_list(SimParams sp, const int* __restrict__ cell_end, const int2* __res
         const float2 xi2 = make_float2(pi.x, pi.x), yi2 = make_float2(pi.y, pi.y), zi2 = make_float2(pi.z, pi.z);
         float wsum = 0.f, wbsum = 0.f;
         int cnt = 0, pend = 0, gword = 0;          // gword: 4-entry words already written to the global list
-        // the candidates are walked tile by tile (one tile at the reference spacing)
-        for (int tile0 = 0; tile0 < G.total; tile0 += TCAP) {
-            const int tile_n = min(TCAP, G.total - tile0);
+        // the candidates are walked tile by tile (one tile at the reference spacing); a ghost cell whose
+        // density does not depend on its neighbours (reference modes) skips the walk altogether
+        const int walk_total = (own || sp.ghost_walk) ? G.total : 0;
+        for (int tile0 = 0; tile0 < walk_total; tile0 += TCAP) {
+            const int tile_n = min(TCAP, walk_total - tile0);
             if (tile0 > 0) __syncthreads();                       // previous tile fully walked
             // ---- stage the tile -------------------------------------------------------------
             const int group = DCHUNK * G.nsplit;                  // candidates per round of all splits
@@ -431,7 +433,7 @@ k_density_list(SimParams sp, const int* __restrict__ cell_end, const int2* __res
             }
             // every split drains completely at the end of a tile: pend == 0 at every tile boundary
         }
-        if (G.total <= 0) __syncthreads();                 // no tile was staged: publish s_row (uniform branch)
+        if (walk_total <= 0) __syncthreads();              // no tile was staged: publish s_row (uniform branch)
         const bool keep_list = s_row >= 0;
         if (keep_list) {
             Lg[(size_t)s_row * NB_THREADS + tid] = make_uint2((unsigned)min(gword, need), 0u);   // count row, in words

@@ -232,17 +232,22 @@ class ShardedSim:
         return self._nsend
 
     def exchange(self):
-        """counts, then records, with both neighbours (torch.distributed)."""
+        """counts, then records, with both neighbours (torch.distributed P2P)."""
         torch, eng, comm = self.torch, self.engine, self.comm
         nl, nr = self._nsend
-        dev = comm.device
-        sc_l = torch.tensor([nl], dtype=torch.int32, device=dev) if self.has_left else None
-        sc_r = torch.tensor([nr], dtype=torch.int32, device=dev) if self.has_right else None
-        rc_l = torch.zeros(1, dtype=torch.int32, device=dev) if self.has_left else None
-        rc_r = torch.zeros(1, dtype=torch.int32, device=dev) if self.has_right else None
-        comm.exchange(self.rank, sc_l, sc_r, rc_l, rc_r)
-        ml = int(rc_l.item()) if self.has_left else 0
-        mr = int(rc_r.item()) if self.has_right else 0
+        if self._counts_dev is None:          # persistent count buffers: [to_left, to_right], [from_left, from_right]
+            self._counts_dev = (torch.zeros(2, dtype=torch.int32, device=comm.device),
+                                torch.zeros(2, dtype=torch.int32, device=comm.device),
+                                torch.zeros(2, dtype=torch.int32).pin_memory() if str(comm.device) != "cpu"
+                                else torch.zeros(2, dtype=torch.int32))
+        snd, rcv, host = self._counts_dev
+        host[0], host[1] = nl, nr
+        snd.copy_(host, non_blocking=True)
+        comm.exchange(self.rank, snd[0:1] if self.has_left else None, snd[1:2] if self.has_right else None,
+                      rcv[0:1] if self.has_left else None, rcv[1:2] if self.has_right else None)
+        ml, mr = rcv.tolist()                  # one synchronisation for both counts
+        ml = ml if self.has_left else 0
+        mr = mr if self.has_right else 0
         comm.exchange(self.rank,
                       eng.message_tensor(SEND_LEFT, nl) if self.has_left and nl else None,
                       eng.message_tensor(SEND_RIGHT, nr) if self.has_right and nr else None,
