@@ -273,6 +273,8 @@ def run_gpu(args):
     l0 = eng.launch_count
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    if sim is not None and sim.profile is not None:
+        sim.profile.clear()
     clocks.mark()
     ev0.record()
     run_steps(args.steps)
@@ -336,6 +338,10 @@ def run_gpu(args):
                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                "api": "ParticleSystemV4.engine.upload_xv + WCSPHV2.step + ParticleSystemV4.dump"}
 
+    if sim is not None and sim.profile:
+        k = max(sim.profile.get("steps", 1), 1)
+        log(f"[bench] rank {rank} host phases per step (ms): " +
+            ", ".join(f"{n} {1e3 * v / k:.3f}" for n, v in sim.profile.items() if n != "steps"))
     if rank != 0:
         return
     # ---- roofline of the dominant kernel, measured live with CUDA events on the engine's stream ----

@@ -225,6 +225,8 @@ class ShardedSim:
         self.global_particle_num = self.parts.total
         self.initial_owned = n_own
         self._counts_dev = None
+        import os
+        self.profile = {} if os.environ.get("TISPH_SHARD_PROFILE") else None
 
     # -- the phases of one step (LocalCluster drives them for several ranks in one process) -----
     def pack(self):
@@ -261,10 +263,20 @@ class ShardedSim:
         self.engine.step(1)
 
     def step(self, nsteps=1):
-        for _ in range(nsteps):
-            self.pack()
-            self.exchange()
-            self.compute()
+        if self.profile is None:
+            for _ in range(nsteps):
+                self.pack()
+                self.exchange()
+                self.compute()
+            return
+        import time
+        for _ in range(nsteps):            # host-side phase times (TISPH_SHARD_PROFILE=1); compute is asynchronous
+            t0 = time.perf_counter(); self.pack()
+            t1 = time.perf_counter(); self.exchange()
+            t2 = time.perf_counter(); self.compute()
+            t3 = time.perf_counter()
+            for k, v in (("pack", t1 - t0), ("exchange", t2 - t1), ("compute_issue", t3 - t2), ("steps", 1)):
+                self.profile[k] = self.profile.get(k, 0.0) + v
 
     # -- state -------------------------------------------------------------------------------
     def save_state(self):
