@@ -79,3 +79,35 @@ def test_nccl_two_gpus():
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
     assert "SHARDED-NCCL-OK" in res.stdout
+
+
+@pytest.mark.parametrize("vmode,dmode", [("reference", "reference"), ("akinci", "summed")])
+def test_local_cluster_with_boundary_particles(vmode, dmode):
+    """a slab of boundary particles under the moving block, cut by the slab faces: rigid points are
+    distributed by x-plane, ghosts carry boundary particles (TISPH_P_HAS_BOUNDARY), akinci volumes
+    and summed densities need two ghost planes"""
+    import copy
+    from ti_sph_b200.sharded import x_plane
+    scene = copy.deepcopy(_scene())
+    g = np.arange(0.28, 0.46, 0.02)
+    slab = np.stack(np.meshgrid(g, [0.26, 0.28], np.arange(0.28, 0.40, 0.02), indexing="ij"), -1).reshape(-1, 3).astype(np.float32)
+    slab = slab[np.argsort(x_plane(slab[:, 0], 0.04), kind="stable")]          # ids follow x-planes (SceneParts)
+    scene["rigidBodies"] = [{"geometryFile": "(points)", "scale": [1, 1, 1], "translation": [0, 0, 0], "rotationAngle": 0,
+                             "rotationAxis": [0, 1, 0], "color": [255, 255, 255], "velocity": [0.0, 0.0, 0.0], "density": 1000.0}]
+    cl = LocalCluster(scene, 3, density_mode=dmode, volume_mode=vmode, rigid_points=[slab])
+    ora = Gen2Oracle(scene, density_mode=dmode, volume_mode=vmode, boundary_points=slab)
+    n = ora.n
+    assert sum(s.engine.particle_num for s in cl.sims) == n
+    for s in range(3):
+        ora.step(); cl.step(1)
+        d = cl.dump()
+        ids = d["orig_id"]
+        assert np.array_equal(np.sort(ids), np.arange(n))
+        inv = np.empty(n, np.int64); inv[ora.orig] = np.arange(n)
+        sel = inv[ids]
+        if s == 0:
+            assert np.array_equal(ids, ora.orig)
+        assert np.array_equal(d["material"], ora.material[sel])
+        assert rel_err(d["position"], ora.x[sel], floor=0.04) < (RTOL if s == 0 else 50 * RTOL)
+    for s in cl.sims:
+        s.engine.sync(); s.engine.close()
