@@ -1,0 +1,98 @@
+"""Full BASELINE sizes on the GPU.
+
+C3 (1 M particles): the whole step against the CPU oracle (the oracle needs ~1 s per step on the
+box's host cores), jittered lattice, both density modes.
+C5 (16 M particles): size-independent properties -- keys recomputed on the host, sortedness,
+histogram / scan consistency, permutation, neighbour counts and density sums of a random sample
+against a float64 KD-tree evaluation, momentum balance of the pair forces, bit-identical replay.
+"""
+import numpy as np
+import pytest
+
+from ti_sph_b200 import _capi as K
+from ti_sph_b200 import scene as sc
+from util import RTOL, jitter, make_pair, rel_err, vec_rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("mode", ["reference", "summed"])
+def test_c3_one_million_particles_against_the_oracle(mode):
+    scene = sc.bench_scene("C3")
+    ora0, eng0 = make_pair(scene)
+    x = jitter(ora0.x, 0.01)
+    eng0.close()
+    ora, eng = make_pair(scene, density_mode=mode, x=x)
+    assert ora.n == 1_000_000
+    t = ora.step(trace=True)
+    eng.stage(K.STAGE_UPDATE)
+    assert np.array_equal(eng.download(K.F_GRID_PARTICLES_NUM), t["scan"])
+    assert np.array_equal(eng.download(K.F_ORIG_ID), t["orig"])
+    eng.stage(K.STAGE_DENSITY)
+    assert np.array_equal(eng.download(K.F_NEIGHBOR_COUNT), t["neighbor_count"])
+    assert rel_err(eng.download(K.F_DENSITY_SUM), t["S"], floor=1.0) < RTOL
+    assert rel_err(eng.download(K.F_DENSITY), t["density"]) < RTOL
+    eng.stage(K.STAGE_FORCE_ADVECT)
+    pfloor = max(9.81, float(np.percentile(np.linalg.norm(t["d_velocity"], axis=1), 99)))
+    assert vec_rel_err(eng.download(K.F_D_VELOCITY), t["d_velocity"], floor=pfloor) < 5 * RTOL
+    vtol = RTOL + 5 * RTOL * 2e-4 * pfloor
+    assert vec_rel_err(eng.download(K.F_V), t["v"], floor=1.0) < vtol
+    assert int(eng.get_param(K.P_STAT_FALLBACK_FORCE)) == 0          # the fast path took everything
+    eng.sync(); eng.close()
+
+
+def test_c5_sixteen_million_particles_properties():
+    from scipy.spatial import cKDTree
+    scene = sc.bench_scene("C5")
+    from core.partice_system.partice_systemv4 import ParticleSystemV4
+    ps = ParticleSystemV4(scene, density_mode="summed")
+    eng = ps.engine
+    n = eng.particle_num
+    assert n == 16_000_000
+    x0 = eng.download(K.F_X)
+    rng = np.random.default_rng(5)
+    x0 = (x0 + rng.uniform(-0.2 * 0.005, 0.2 * 0.005, size=x0.shape)).astype(np.float32)   # off the knife edges
+    eng.upload_xv(x0, eng.download(K.F_V))
+    eng.save_state()
+    eng.set_param(K.P_DIAGNOSTICS, 1)
+    # ---- ps.update()
+    eng.stage(K.STAGE_UPDATE)
+    keys, xs = eng.download(K.F_GRID_IDS), eng.download(K.F_X)
+    h = np.float32(0.02)
+    cell = (xs / h).astype(np.int32)
+    g = ps.grid_num.astype(np.int64)
+    assert np.array_equal(keys, (cell[:, 0] * g[1] * g[2] + cell[:, 1] * g[2] + cell[:, 2]).astype(np.int32))
+    assert np.all(np.diff(keys) >= 0)                                             # sorted by cell key
+    scan, hist = eng.download(K.F_GRID_PARTICLES_NUM), eng.download(K.F_CELL_COUNT)
+    assert scan[-1] == n and hist.sum() == n and np.array_equal(np.cumsum(hist, dtype=np.int64), scan)
+    ids = eng.download(K.F_ORIG_ID)
+    assert np.array_equal(np.sort(ids), np.arange(n, dtype=np.int32))             # a permutation
+    assert np.array_equal(xs, x0[ids])                                            # records moved intact
+    seg = np.nonzero(np.diff(keys) == 0)[0]
+    assert np.all(ids[seg + 1] > ids[seg])                                        # stable inside every cell
+    # ---- density: a random sample against float64
+    eng.stage(K.STAGE_DENSITY)
+    nc, S = eng.download(K.F_NEIGHBOR_COUNT), eng.download(K.F_DENSITY_SUM)
+    assert nc.sum() % 2 == 0                                                      # neighbourhood is symmetric
+    tree = cKDTree(xs.astype(np.float64))
+    sample = rng.choice(n, 3000, replace=False)
+    kw = 8 / np.pi / 0.02 ** 3
+    mass = np.float64(np.float32(0.8 * 0.01 ** 3) * np.float32(1000.0))
+    for i, nb in zip(sample, tree.query_ball_point(xs[sample].astype(np.float64), 0.02 * (1 - 1e-6))):
+        nb = np.array([j for j in nb if j != i])
+        q = np.linalg.norm(xs[nb].astype(np.float64) - xs[i], axis=1) / 0.02
+        w = np.where(q <= 0.5, 6 * (q ** 3 - q ** 2) + 1, 2 * (1 - q) ** 3)
+        assert abs(nc[i] - len(nb)) <= 1                                          # f32 vs f64 at the cutoff
+        assert abs(S[i] - mass * kw * w.sum()) <= 2e-5 * max(S[i], 1.0)
+    # ---- forces: the pair forces are antisymmetric, so the total momentum change vanishes
+    eng.stage(K.STAGE_FORCE_ADVECT)
+    a_p = eng.download(K.F_A_PRESSURE).astype(np.float64)
+    assert np.linalg.norm(a_p.sum(axis=0)) < 1e-6 * np.abs(a_p).sum()
+    out1 = (eng.download(K.F_X), eng.download(K.F_V))
+    # ---- replay from the checkpoint: bit-identical
+    eng.restore_state()
+    eng.step(1)
+    out2 = (eng.download(K.F_X), eng.download(K.F_V))
+    assert np.array_equal(out1[0], out2[0]) and np.array_equal(out1[1], out2[1])
+    assert int(eng.get_param(K.P_STAT_FALLBACK_FORCE)) == 0
+    eng.sync(); eng.close()

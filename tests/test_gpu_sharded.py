@@ -111,3 +111,19 @@ def test_local_cluster_with_boundary_particles(vmode, dmode):
         assert rel_err(d["position"], ora.x[sel], floor=0.04) < (RTOL if s == 0 else 50 * RTOL)
     for s in cl.sims:
         s.engine.sync(); s.engine.close()
+
+
+def test_local_cluster_one_million_particles():
+    """C3 (1 M particles) cut into 4 slabs: one step bit-identical in order, 1e-5 in fields"""
+    from ti_sph_b200 import scene as sc
+    scene = sc.bench_scene("C3")
+    cl = LocalCluster(scene, 4)
+    ora = Gen2Oracle(scene)
+    ora.step(); cl.step(1)
+    d = cl.dump()
+    assert np.array_equal(d["orig_id"], ora.orig)
+    assert rel_err(d["position"], ora.x, floor=0.04) < RTOL
+    assert vec_rel_err(d["velocity"], ora.v, floor=1.0) < 5 * RTOL
+    assert all(int(s.engine.get_param(K.P_STAT_FALLBACK_FORCE)) == 0 for s in cl.sims)
+    for s in cl.sims:
+        s.engine.sync(); s.engine.close()
