@@ -258,11 +258,12 @@ __device__ __forceinline__ void sts_u16(uint32_t a, uint32_t v) {
 constexpr int DCHUNK = 16;                                    // candidates filtered between drain checks
 constexpr int O_DUMMY = 8 * (TCAP / 2);
 constexpr int E_DUMMY = TCAP;
-constexpr uint32_t E_NONE = 0xffffu;                          // list entry that names no candidate (padding)
-constexpr int MAX_TOTAL = 0xfff0;                             // candidate indices of an item must fit 16 bits
+// A neighbour-list entry is (tile number << 11) | slot: slots of a tile are 0 .. TCAP-1 (swizzled
+// candidate slots, cand_slot) plus E_DUMMY = TCAP, the always-FAR padding candidate of every tile.
+constexpr int TSHIFT = 11;
+constexpr int MAX_TOTAL = (0x10000 >> TSHIFT) * TCAP;         // 32 tiles: entries must fit 16 bits
 constexpr size_t DL_SMEM = (size_t)(TCAP / 2 + 1) * 32 + (size_t)LCAP * NB_THREADS * sizeof(unsigned short);
 
-__device__ __forceinline__ uint32_t o_to_e(uint32_t o) { return ((o >> 2) & ~1u) | (o & 1u); }
 
 // Split s of an item walks the candidate pairs s, s + nsplit, s + 2 nsplit, ... of the tile (pair-wise
 // interleave keeps the splits' survivor counts balanced on lattice-like states).  In shared memory
@@ -276,8 +277,8 @@ __device__ __forceinline__ int pair_slot(int p, int nsplit) {       // nsplit is
 // swizzled slot of tile candidate e (used as the candidate's name in the neighbour lists)
 __device__ __forceinline__ int cand_slot(int e, int nsplit) { return 2 * pair_slot(e >> 1, nsplit) + (e & 1); }
 
-// Filter 8 consecutive pair slots and push the survivors' pair offsets.
-__device__ __forceinline__ void filter8(uint32_t a0, uint32_t o0, float2 xi2, float2 yi2, float2 zi2,
+// Filter 8 consecutive pair slots and push the survivors' candidate slots (2 * pair slot + 0|1).
+__device__ __forceinline__ void filter8(uint32_t a0, uint32_t e0, float2 xi2, float2 yi2, float2 zi2,
                                         float cut_wide, uint32_t sL, int& pend) {
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
@@ -287,8 +288,8 @@ __device__ __forceinline__ void filter8(uint32_t a0, uint32_t o0, float2 xi2, fl
         float2 dy = __fadd2_rn(yi2, make_float2(c.z, c.w));
         float2 dz = __fadd2_rn(zi2, cz);
         float2 s = __ffma2_rn(dz, dz, __ffma2_rn(dy, dy, __fmul2_rn(dx, dx)));
-        if (s.x < cut_wide) { sts_u16(sL + pend * (2 * NB_THREADS), o0 + 8u * k); ++pend; }
-        if (s.y < cut_wide) { sts_u16(sL + pend * (2 * NB_THREADS), o0 + 8u * k + 1u); ++pend; }
+        if (s.x < cut_wide) { sts_u16(sL + pend * (2 * NB_THREADS), e0 + 2u * k); ++pend; }
+        if (s.y < cut_wide) { sts_u16(sL + pend * (2 * NB_THREADS), e0 + 2u * k + 1u); ++pend; }
     }
 }
 
@@ -313,7 +314,7 @@ k_density_list(SimParams sp, const int* __restrict__ cell_end, const int2* __res
     const float cut_wide = sp.d2_cut * 1.000001f;       // superset filter; the drain applies the exact test
     const uint32_t sT = smem_u32(T);
     const uint32_t sL = smem_u32(L) + 2u * tid;         // my pending list: slot k at sL + k * 2 * NB_THREADS
-    for (int k = 0; k < LCAP; ++k) L[k * NB_THREADS + tid] = (unsigned short)O_DUMMY;
+    for (int k = 0; k < LCAP; ++k) L[k * NB_THREADS + tid] = (unsigned short)E_DUMMY;
     if (tid < 2) T[TCAP + tid] = tid == 0 ? make_float4(FAR, FAR, FAR, FAR) : make_float4(FAR, FAR, __int_as_float(MAT_FLUID), __int_as_float(MAT_FLUID));
 
     for (;;) {
@@ -385,43 +386,43 @@ k_density_list(SimParams sp, const int* __restrict__ cell_end, const int2* __res
             __syncthreads();
             // ---- walk -----------------------------------------------------------------------
             const bool keep_list = s_row >= 0;                    // (written by thread 0 before the barrier)
+            const int self_r = self_t - tile0;                    // my own slot in this tile, if any
+            const uint32_t self_e = (self_r >= 0 && self_r < TCAP) ? (uint32_t)cand_slot(self_r, G.nsplit) : 0xffffffffu;
             uint2* gl = Lg + (size_t)(keep_list ? s_row + 1 : 0) * NB_THREADS + tid;
-            const int self_r = self_t - tile0;
-            const uint32_t self_o = (self_r >= 0 && self_r < TCAP)
-                                        ? (uint32_t)(8 * pair_slot(self_r >> 1, G.nsplit) + (self_r & 1)) : 0xffffffffu;
             const int mtot = npair / G.nsplit;                    // my pairs in this tile: split, split + nsplit, ...
             for (int m0 = 0; m0 < mtot; m0 += DCHUNK / 2) {
                 const uint32_t p0 = (uint32_t)(split * ((TCAP / 2) >> (G.nsplit == 4 ? 2 : 3)) + m0);   // first pair slot of the chunk
-                filter8(sT + 32u * p0, 8u * p0, xi2, yi2, zi2, cut_wide, sL, pend);
+                filter8(sT + 32u * p0, 2u * p0, xi2, yi2, zi2, cut_wide, sL, pend);
                 const bool last = m0 + DCHUNK / 2 >= mtot;        // my last chunk of this tile
                 if (last || __any_sync(0xffffffffu, pend > LCAP - DCHUNK)) {
                     // ---- drain: whole words of 4 entries; a remainder waits for the next round, the
-                    //      last round of a tile pads with the dummy candidate.  Branch-free per entry:
-                    //      the self entry and slots beyond this lane's count are redirected to the
-                    //      dummy candidate, whose distance is FAR (q clamps to 1, W = 0, not counted).
+                    //      last round of a tile pads with the tile's dummy candidate (FAR: q clamps to 1,
+                    //      W = 0, not counted).  Branch-free per entry; every lane runs its own word
+                    //      count.  The self pair stays in the list (it contributes exact zeros to the
+                    //      force walk); its W is masked and its count is taken out at the end.
                     const int nd = last ? (pend + 3) & ~3 : pend & ~3;
-                    const int lim = last ? pend : nd;                     // entries that are mine to evaluate now
-                    const int nd_max = __reduce_max_sync(0xffffffffu, nd);
+                    if (last)
+                        for (int k = pend; k < nd; ++k) sts_u16(sL + k * (2 * NB_THREADS), E_DUMMY);
                     uint2* gp = gl + (size_t)gword * NB_THREADS;
                     const int groom = keep_list ? need - gword : 0;       // words that still fit the item's list rows
-                    for (int k4 = 0; k4 < nd_max; k4 += 4, gp += NB_THREADS) {
+                    const uint32_t tbase = (uint32_t)(tile0 / TCAP) << TSHIFT;
+                    for (int k4 = 0; k4 < nd; k4 += 4, gp += NB_THREADS) {
                         uint32_t ew[4];
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
-                            uint32_t o = lds_u16(sL + (k4 + j) * (2 * NB_THREADS));
-                            const bool real = k4 + j < lim && o != self_o;
-                            o = real ? o : (uint32_t)O_DUMMY;
-                            const uint32_t a = sT + 4u * o;
+                            const uint32_t e = lds_u16(sL + (k4 + j) * (2 * NB_THREADS));
+                            const uint32_t a = sT + ((e & ~1u) << 4) + ((e & 1u) << 2);   // pair slot * 32 + lane * 4
                             const float dx = pi.x + lds_f32(a), dy = pi.y + lds_f32(a + 8), dz = pi.z + lds_f32(a + 16);
                             const float d2 = dist2_exact(dx, dy, dz);
                             const float r = d2 * rsqrt_approx(fmaxf(d2, 1e-30f));
-                            const float w = spline_w(fminf(r * sp.inv_h, 1.0f));
+                            float w = spline_w(fminf(r * sp.inv_h, 1.0f));
+                            w = e == self_e ? 0.f : w;            // p_i != p_j (the count is corrected at the end)
                             wsum += w;
-                            cnt += d2 < sp.d2_cut ? 1 : 0;
+                            if (d2 < sp.d2_cut) ++cnt;
                             if (AKINCI) wbsum += __float_as_int(lds_f32(a + 24)) == MAT_BOUNDARY ? w : 0.f;
-                            ew[j] = real ? (uint32_t)tile0 + o_to_e(o) : E_NONE;
+                            ew[j] = tbase | e;
                         }
-                        if (k4 < nd && (k4 >> 2) < groom)
+                        if ((k4 >> 2) < groom)
                             *gp = make_uint2(ew[0] | (ew[1] << 16), ew[2] | (ew[3] << 16));
                     }
                     gword += nd >> 2;
@@ -453,7 +454,9 @@ k_density_list(SimParams sp, const int* __restrict__ cell_end, const int2* __res
                 wbsum += red_b[s * G.tl + t_local];
                 cnt += red_c[s * G.tl + t_local];
             }
-            density_epilogue(sp, i, pi.w, __float_as_int(Q[i].z), wsum, wbsum, cnt, V, Q, D, S, ncount);
+            const int mat_i = __float_as_int(Q[i].z);
+            if (self_t >= 0 && walk_total > 0) cnt -= 1;   // the self pair was counted (p_i != p_j, partice_systemv4.py:344)
+            density_epilogue(sp, i, pi.w, mat_i, wsum, wbsum, cnt, V, Q, D, S, ncount);
         }
     }
 }
@@ -585,7 +588,7 @@ k_force_list(SimParams sp, const int* __restrict__ cell_end, const int2* __restr
                 const uint32_t e4[4] = {cur.x & 0xffffu, cur.x >> 16, cur.y & 0xffffu, cur.y >> 16};
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    const uint32_t e = min(e4[j], (uint32_t)E_DUMMY);      // E_NONE -> dummy candidate
+                    const uint32_t e = e4[j];                              // slot of tile 0 (or its dummy)
                     const uint32_t a = sP + 16u * e;
                     const float4 pj = lds_f32x4(a);
                     const float4 vj = lds_f32x4(a + V_OFF);
@@ -600,6 +603,7 @@ k_force_list(SimParams sp, const int* __restrict__ cell_end, const int2* __restr
             int k = 0;
             for (int tile0 = 0; tile0 < G.total; tile0 += TCAP) {
                 const int tile_n = min(TCAP, G.total - tile0);
+                const uint32_t tbase = (uint32_t)(tile0 / TCAP) << TSHIFT;
                 if (tile0 > 0) __syncthreads();
                 stage_force_tile(R, tile0, tile_n, tile_n, G.nsplit, Pin, Vin, Qin, D, tP, tV, tR);
                 __syncthreads();
@@ -608,9 +612,9 @@ k_force_list(SimParams sp, const int* __restrict__ cell_end, const int2* __restr
                     bool done = true;                          // every real entry of the word lies below the tile's end
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                        const uint32_t rel = e4[j] - (uint32_t)tile0;
-                        const uint32_t e = rel < (uint32_t)TCAP ? rel : (uint32_t)E_DUMMY;
-                        done = done && (e4[j] == E_NONE || e4[j] < (uint32_t)(tile0 + TCAP));
+                        const uint32_t rel = e4[j] - tbase;
+                        const uint32_t e = rel < (1u << TSHIFT) ? rel : (uint32_t)E_DUMMY;
+                        done = done && e4[j] < tbase + (1u << TSHIFT);
                         const uint32_t a = sP + 16u * e;
                         const float4 pj = lds_f32x4(a);
                         const float4 vj = lds_f32x4(a + V_OFF);
