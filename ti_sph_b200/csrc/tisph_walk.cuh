@@ -280,16 +280,26 @@ __device__ __forceinline__ int cand_slot(int e, int nsplit) { return 2 * pair_sl
 // Filter 8 consecutive pair slots and push the survivors' candidate slots (2 * pair slot + 0|1).
 __device__ __forceinline__ void filter8(uint32_t a0, uint32_t e0, float2 xi2, float2 yi2, float2 zi2,
                                         float cut_wide, uint32_t sL, int& pend) {
+    // loads are issued four pairs ahead of their use: shared-memory stores (the pushes) and loads keep
+    // their program order, so an unbatched loop would expose one LDS latency per pair
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        const float4 c = lds_f32x4(a0 + 32u * k);
-        const float2 cz = lds_f32x2(a0 + 32u * k + 16u);
-        float2 dx = __fadd2_rn(xi2, make_float2(c.x, c.y));
-        float2 dy = __fadd2_rn(yi2, make_float2(c.z, c.w));
-        float2 dz = __fadd2_rn(zi2, cz);
-        float2 s = __ffma2_rn(dz, dz, __ffma2_rn(dy, dy, __fmul2_rn(dx, dx)));
-        if (s.x < cut_wide) { sts_u16(sL + pend * (2 * NB_THREADS), e0 + 2u * k); ++pend; }
-        if (s.y < cut_wide) { sts_u16(sL + pend * (2 * NB_THREADS), e0 + 2u * k + 1u); ++pend; }
+    for (int b = 0; b < 8; b += 4) {
+        float4 c[4];
+        float2 cz[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            c[k] = lds_f32x4(a0 + 32u * (b + k));
+            cz[k] = lds_f32x2(a0 + 32u * (b + k) + 16u);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            float2 dx = __fadd2_rn(xi2, make_float2(c[k].x, c[k].y));
+            float2 dy = __fadd2_rn(yi2, make_float2(c[k].z, c[k].w));
+            float2 dz = __fadd2_rn(zi2, cz[k]);
+            float2 s = __ffma2_rn(dz, dz, __ffma2_rn(dy, dy, __fmul2_rn(dx, dx)));
+            if (s.x < cut_wide) { sts_u16(sL + pend * (2 * NB_THREADS), e0 + 2u * (b + k)); ++pend; }
+            if (s.y < cut_wide) { sts_u16(sL + pend * (2 * NB_THREADS), e0 + 2u * (b + k) + 1u); ++pend; }
+        }
     }
 }
 
