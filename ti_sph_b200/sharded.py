@@ -182,6 +182,62 @@ class TorchDistComm:
         return out
 
 
+class ShmCounts:
+    """Halo record counts exchanged through a POSIX shared-memory segment instead of a device
+    round trip: every rank of ONE node publishes (step, to_left, to_right) and polls its
+    neighbours' slots.  Costs microseconds and no stream synchronisation; used when all ranks
+    live on this node (LOCAL_WORLD_SIZE == WORLD_SIZE), the NCCL path otherwise."""
+
+    def __init__(self, comm, rank, world):
+        import os
+        from multiprocessing import shared_memory
+        self.rank, self.world = rank, world
+        name = None
+        if rank == 0:
+            self.shm = shared_memory.SharedMemory(create=True, size=world * 64)
+            self.shm.buf[:world * 64] = bytes(world * 64)
+            name = self.shm.name
+        name = comm.all_gather_objects(name)[0]
+        if rank != 0:
+            self.shm = shared_memory.SharedMemory(name=name)
+        # two slots per rank, used alternately: a rank can be at most one step ahead of a neighbour
+        # (it needs the neighbour's counts of step k+1 before it can publish step k+2)
+        self.arr = np.ndarray((world, 2, 4), dtype=np.int64, buffer=self.shm.buf)
+        self.step = 0
+        comm.all_gather_objects(None)          # everybody attached before anybody publishes
+        import atexit
+        atexit.register(self.close)
+
+    def exchange(self, nl, nr, has_left, has_right):
+        import time
+        self.step += 1
+        slot = self.step & 1
+        me = self.arr[self.rank, slot]
+        me[1], me[2] = nl, nr
+        me[0] = self.step                      # publish last (x86: stores are not reordered)
+        ml = mr = 0
+        t0 = time.perf_counter()
+        for nb, col, flag in ((self.rank - 1, 2, has_left), (self.rank + 1, 1, has_right)):
+            if not flag:
+                continue
+            while self.arr[nb, slot, 0] != self.step:
+                if time.perf_counter() - t0 > 120.0:
+                    raise RuntimeError("halo count exchange timed out (a neighbour rank died?)")
+            if nb < self.rank:
+                ml = int(self.arr[nb, slot, col])
+            else:
+                mr = int(self.arr[nb, slot, col])
+        return ml, mr
+
+    def close(self):
+        try:
+            self.shm.close()
+            if self.rank == 0:
+                self.shm.unlink()
+        except Exception:
+            pass
+
+
 # ------------------------------------------------------------------------------ one rank
 class ShardedSim:
     """One rank's slab of a gen-2 (ParticleSystemV4 + WCSPHV2) simulation."""
@@ -225,7 +281,11 @@ class ShardedSim:
         self.global_particle_num = self.parts.total
         self.initial_owned = n_own
         self._counts_dev = None
+        self._shm = None
         import os
+        if comm is not None and world > 1 and os.environ.get("TISPH_SHM_COUNTS", "1") != "0" and \
+                os.environ.get("LOCAL_WORLD_SIZE", str(world)) == str(world):
+            self._shm = ShmCounts(comm, rank, world)
         self.profile = {} if os.environ.get("TISPH_SHARD_PROFILE") else None
 
     # -- the phases of one step (LocalCluster drives them for several ranks in one process) -----
@@ -242,14 +302,17 @@ class ShardedSim:
                                 torch.zeros(2, dtype=torch.int32, device=comm.device),
                                 torch.zeros(2, dtype=torch.int32).pin_memory() if str(comm.device) != "cpu"
                                 else torch.zeros(2, dtype=torch.int32))
-        snd, rcv, host = self._counts_dev
-        host[0], host[1] = nl, nr
-        snd.copy_(host, non_blocking=True)
-        comm.exchange(self.rank, snd[0:1] if self.has_left else None, snd[1:2] if self.has_right else None,
-                      rcv[0:1] if self.has_left else None, rcv[1:2] if self.has_right else None)
-        ml, mr = rcv.tolist()                  # one synchronisation for both counts
-        ml = ml if self.has_left else 0
-        mr = mr if self.has_right else 0
+        if self._shm is not None:
+            ml, mr = self._shm.exchange(nl, nr, self.has_left, self.has_right)
+        else:
+            snd, rcv, host = self._counts_dev
+            host[0], host[1] = nl, nr
+            snd.copy_(host, non_blocking=True)
+            comm.exchange(self.rank, snd[0:1] if self.has_left else None, snd[1:2] if self.has_right else None,
+                          rcv[0:1] if self.has_left else None, rcv[1:2] if self.has_right else None)
+            ml, mr = rcv.tolist()                  # one synchronisation for both counts
+            ml = ml if self.has_left else 0
+            mr = mr if self.has_right else 0
         comm.exchange(self.rank,
                       eng.message_tensor(SEND_LEFT, nl) if self.has_left and nl else None,
                       eng.message_tensor(SEND_RIGHT, nr) if self.has_right and nr else None,
