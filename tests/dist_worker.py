@@ -30,6 +30,7 @@ def main():
                 sim.step(1)
                 sim.dump()
         sim.engine.sync()
+        sim.engine.close()
     dist.barrier()
     if rank == 0:
         print("SHARDED-NCCL-OK")

@@ -77,6 +77,10 @@ def test_nccl_two_gpus():
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
            "--master-addr", "127.0.0.1", "--master-port", "29611", os.path.join(HERE, "dist_worker.py")]
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    if res.returncode != 0 or "SHARDED-NCCL-OK" not in res.stdout:
+        os.makedirs(os.path.join(os.path.dirname(HERE), "gpurun_out"), exist_ok=True)
+        with open(os.path.join(os.path.dirname(HERE), "gpurun_out", "nccl_worker_failure.log"), "w") as fh:
+            fh.write(res.stdout + "\n----- stderr -----\n" + res.stderr)
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
     assert "SHARDED-NCCL-OK" in res.stdout
 

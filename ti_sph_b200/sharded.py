@@ -200,6 +200,11 @@ class ShmCounts:
         name = comm.all_gather_objects(name)[0]
         if rank != 0:
             self.shm = shared_memory.SharedMemory(name=name)
+            try:        # Python < 3.13 registers attached segments for unlinking too; only the creator unlinks
+                from multiprocessing import resource_tracker
+                resource_tracker.unregister(self.shm._name, "shared_memory")
+            except Exception:
+                pass
         # two slots per rank, used alternately: a rank can be at most one step ahead of a neighbour
         # (it needs the neighbour's counts of step k+1 before it can publish step k+2)
         self.arr = np.ndarray((world, 2, 4), dtype=np.int64, buffer=self.shm.buf)
