@@ -226,12 +226,11 @@ def run_gpu(args):
         sim = None
     else:
         from ti_sph_b200.sharded import ShardedSim, TorchDistComm
-        stream = torch.cuda.Stream()
-        torch.cuda.set_stream(stream)
         sim = ShardedSim(scene, rank, world, comm=TorchDistComm(device=f"cuda:{local_rank}"),
                          density_mode=args.mode, device=local_rank)
         eng = sim.engine
-        eng.set_stream(stream.cuda_stream)
+        stream = sim.stream                # engine kernels and NCCL exchanges are ordered on this stream
+        torch.cuda.set_stream(stream)      # ... and so are the timing events
         n_total = sim.global_particle_num
         log(f"[bench] rank {rank}: planes [{sim.plane_lo},{sim.plane_hi}) {sim.initial_owned} particles")
         step = lambda k=1: sim.step(k)
@@ -298,24 +297,23 @@ def run_gpu(args):
         launches = int(lt.item())
     value = n_total / (ms * 1e-3)
 
-    # ---- end-to-end through the drop-in classes, host buffers ------------------------------
-    e2e = None
-    if world == 1:
-        n = n_total
-        e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    # ---- end-to-end through the public API, host buffers ---------------------------------------
+    # every step: this step's input state (x, v) goes host -> device from pinned memory, step(),
+    # and the step's result (position / velocity / material / colour [+ ids when sharded]) comes back.
+    dbg = os.environ.get("BENCH_DEBUG")
+
+    def pinned(shape, dtype):
+        return torch.empty(shape, dtype=torch.float32 if dtype == np.float32 else torch.int32).pin_memory().numpy()
+
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    if sim is None:
         eng.restore_state()
         host = ps.dump()
-
-        def pinned(a):
-            return torch.empty(a.shape, dtype=torch.float32 if a.dtype == np.float32 else torch.int32).pin_memory().numpy()
-
-        hx, hv = pinned(host["position"]), pinned(host["velocity"])      # the step's input, on the host
+        hx, hv = pinned(host["position"].shape, np.float32), pinned(host["velocity"].shape, np.float32)
         hx[:] = host["position"]; hv[:] = host["velocity"]
-        outs = {k: pinned(v) for k, v in host.items()}                    # the step's result, on the host
+        outs = {k: pinned(v.shape, v.dtype) for k, v in host.items()}
         h2d = hx.nbytes + hv.nbytes
         d2h = sum(v.nbytes for v in outs.values())
-
-        dbg = os.environ.get("BENCH_DEBUG")
 
         def e2e_step():
             t0 = time.time()
@@ -323,20 +321,45 @@ def run_gpu(args):
             if dbg: eng.sync(); log(f"[e2e] upload {time.time() - t0:.3f}s")
             solver.step()
             if dbg: eng.sync(); log(f"[e2e] step {time.time() - t0:.3f}s")
-            ps.dump(out=outs)              # device -> host: the step's result (position/velocity/material/color)
+            ps.dump(out=outs)              # device -> host: the step's result
             if dbg: log(f"[e2e] dump {time.time() - t0:.3f}s")
+        api = "ParticleSystemV4.engine.upload_xv + WCSPHV2.step + ParticleSystemV4.dump"
+    else:
+        sim.restore_state()
+        rows = int(1.25 * eng.particle_num) + 4096
+        px, pv = pinned((rows, 3), np.float32), pinned((rows, 3), np.float32)
 
+        def dump_pinned():
+            k = eng.particle_num           # the owned set changes as particles migrate
+            return sim.dump_local(out={"position": px[:k], "velocity": pv[:k]})
+        state = {"d": dump_pinned()}
+        bytes_io = [0, 0]
+
+        def e2e_step():
+            d = state["d"]                 # the previous result is this step's input (same owned set)
+            sim.upload_xv(d["position"], d["velocity"])
+            sim.step(1)
+            state["d"] = dump_pinned()
+            bytes_io[0] = d["position"].nbytes + d["velocity"].nbytes
+            bytes_io[1] = sum(state["d"][k].nbytes for k in ("position", "velocity", "material", "orig_id"))
+        api = "ShardedSim.upload_xv + ShardedSim.step + ShardedSim.dump_local (per rank; bytes summed over ranks)"
+    e2e_step()
+    barrier()
+    ev0.record()
+    for _ in range(e2e_steps):
         e2e_step()
-        barrier()
-        ev0.record()
-        for _ in range(e2e_steps):
-            e2e_step()
-        ev1.record()
-        barrier()
-        ems = ev0.elapsed_time(ev1) / e2e_steps
-        e2e = {"value": n / (ems * 1e-3), "unit": UNIT, "ms_per_step": ems, "steps": e2e_steps,
-               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-               "api": "ParticleSystemV4.engine.upload_xv + WCSPHV2.step + ParticleSystemV4.dump"}
+    ev1.record()
+    barrier()
+    ems = ev0.elapsed_time(ev1) / e2e_steps
+    if sim is not None:
+        import torch.distributed as dist
+        t = torch.tensor([ems, float(bytes_io[0]), float(bytes_io[1])], device="cuda", dtype=torch.float64)
+        tm = t.clone()
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        ems, h2d, d2h = float(tm[0].item()), int(t[1].item()), int(t[2].item())
+    e2e = {"value": n_total / (ems * 1e-3), "unit": UNIT, "ms_per_step": ems, "steps": e2e_steps,
+           "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "api": api}
 
     if sim is not None and sim.profile:
         k = max(sim.profile.get("steps", 1), 1)
@@ -387,8 +410,7 @@ def run_gpu(args):
                    "parallelism": "single GPU" if world == 1 else f"x-slabs x{world}, halo exchange over NCCL"},
         "clocks": clk, "gpu_launches": int(launches), "roofline": roofline,
     }
-    if e2e is not None:
-        line["e2e"] = e2e
+    line["e2e"] = e2e
     if cpu is not None:
         line["cpu_baseline"] = cpu
     print(json.dumps(line), flush=True)

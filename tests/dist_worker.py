@@ -22,7 +22,6 @@ def main():
     for mode in ("reference", "summed"):
         sim = ShardedSim(_scene(), rank, world, comm=TorchDistComm(device=f"cuda:{local}"),
                          density_mode=mode, device=local)
-        sim.engine.set_stream(torch.cuda.current_stream().cuda_stream)
         if rank == 0:
             check_against_oracle(lambda: sim.step(1), sim.dump, mode)
         else:

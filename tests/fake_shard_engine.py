@@ -111,7 +111,7 @@ class FakeShardEngine:
         blank["rigidBodies"] = []
         return Gen2Oracle(blank, density_mode=mode, volume_mode=vmode)
 
-    def download(self, field):
+    def download(self, field, out=None):
         return {K.F_X: self.x, K.F_V: self.v, K.F_MATERIAL: self.material, K.F_ORIG_ID: self.orig,
                 K.F_DENSITY: self.density, K.F_PRESSURE: self.pressure}[field].copy()
 

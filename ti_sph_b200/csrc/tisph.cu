@@ -653,15 +653,16 @@ int tisph_download(tisph_ctx* c, int32_t field, void* dst, size_t bytes) {
 int tisph_upload_xv(tisph_ctx* c, const float* pos, const float* vel) {
     CHECK_CTX(c);
     if (!pos || !vel) return fail(TISPH_ERR_INVALID, "null argument");
-    if (c->phase != 0) return fail(TISPH_ERR_INVALID, "cannot upload in the middle of a step");
-    int n = c->n, dim = c->cfg.dim;
+    if (c->phase != 0 || c->appended) return fail(TISPH_ERR_INVALID, "cannot upload in the middle of a step");
+    { int rc = ensure_range(c); if (rc) return rc; }
+    int n = c->o_hi - c->o_lo, dim = c->cfg.dim;          // the owned particles (all of them unless sharded)
     if (n == 0) return TISPH_OK;
     cudaStream_t st = c->stream;
     float* d_pos = (float*)c->staging;
     float* d_vel = d_pos + (size_t)n * dim;
     CU(cudaMemcpyAsync(d_pos, pos, (size_t)n * dim * 4, cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(d_vel, vel, (size_t)n * dim * 4, cudaMemcpyHostToDevice, st));
-    k_upload_xv<<<nblocks(n, 256), 256, 0, st>>>(n, dim, d_pos, d_vel, c->P[c->cur], c->V[c->cur]);
+    k_upload_xv<<<nblocks(n, 256), 256, 0, st>>>(n, dim, d_pos, d_vel, c->P[c->cur] + c->o_lo, c->V[c->cur] + c->o_lo);
     c->launches += 1;
     CU(cudaGetLastError());
     return TISPH_OK;

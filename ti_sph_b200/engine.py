@@ -76,6 +76,7 @@ class Engine:
         check(self._lib.tisph_state_restore(self._ctx))
 
     def upload_xv(self, pos, vel):
+        """overwrite x and v of the (owned) particles in their current order"""
         n = self.particle_num
         pos = np.ascontiguousarray(pos, np.float32).reshape(n, self.dim)
         vel = np.ascontiguousarray(vel, np.float32).reshape(n, self.dim)

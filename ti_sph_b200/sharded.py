@@ -200,11 +200,8 @@ class ShmCounts:
         name = comm.all_gather_objects(name)[0]
         if rank != 0:
             self.shm = shared_memory.SharedMemory(name=name)
-            try:        # Python < 3.13 registers attached segments for unlinking too; only the creator unlinks
-                from multiprocessing import resource_tracker
-                resource_tracker.unregister(self.shm._name, "shared_memory")
-            except Exception:
-                pass
+            # (Python < 3.13 also registers attached segments with the resource tracker, which prints a
+            # harmless "leaked shared_memory" warning at exit; only the creator unlinks.)
         # two slots per rank, used alternately: a rank can be at most one step ahead of a neighbour
         # (it needs the neighbour's counts of step k+1 before it can publish step k+2)
         self.arr = np.ndarray((world, 2, 4), dtype=np.int64, buffer=self.shm.buf)
@@ -287,6 +284,13 @@ class ShardedSim:
         self.initial_owned = n_own
         self._counts_dev = None
         self._shm = None
+        # The engine and the NCCL exchanges must be ordered on ONE stream: the exchange's wait() only
+        # blocks the stream that is current when it is posted.  (Handing the engine torch's legacy
+        # default stream would not do: its handle is 0, which tisph_set_stream reads as "own stream".)
+        self.stream = None
+        if comm is not None and str(getattr(comm, "device", "cpu")).startswith("cuda"):
+            self.stream = torch.cuda.Stream(device=comm.device)
+            eng.set_stream(self.stream.cuda_stream)
         import os
         if comm is not None and world > 1 and os.environ.get("TISPH_SHM_COUNTS", "1") != "0" and \
                 os.environ.get("LOCAL_WORLD_SIZE", str(world)) == str(world):
@@ -300,6 +304,12 @@ class ShardedSim:
 
     def exchange(self):
         """counts, then records, with both neighbours (torch.distributed P2P)."""
+        if self.stream is not None and self.torch.cuda.current_stream(self.stream.device) != self.stream:
+            with self.torch.cuda.stream(self.stream):
+                return self._exchange()
+        return self._exchange()
+
+    def _exchange(self):
         torch, eng, comm = self.torch, self.engine, self.comm
         nl, nr = self._nsend
         if self._counts_dev is None:          # persistent count buffers: [to_left, to_right], [from_left, from_right]
@@ -353,11 +363,16 @@ class ShardedSim:
     def restore_state(self):
         self.engine.restore_state()
 
-    def dump_local(self):
-        """this rank's owned particles, in sorted order (keys of dump() + 'orig_id')"""
-        e = self.engine
+    def upload_xv(self, pos, vel):
+        """overwrite x, v of this rank's owned particles (order of dump_local) from host arrays"""
+        self.engine.upload_xv(pos, vel)
+
+    def dump_local(self, out=None):
+        """this rank's owned particles, in sorted order (keys of dump() + 'orig_id'); `out` may hold
+        preallocated (pinned) arrays for 'position' and 'velocity'"""
+        e, out = self.engine, out or {}
         ids = e.download(K.F_ORIG_ID)
-        return {"position": e.download(K.F_X), "velocity": e.download(K.F_V),
+        return {"position": e.download(K.F_X, out.get("position")), "velocity": e.download(K.F_V, out.get("velocity")),
                 "material": e.download(K.F_MATERIAL), "color": self.parts.color_of(ids), "orig_id": ids}
 
     def dump(self):
