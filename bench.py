@@ -331,7 +331,7 @@ def run_gpu(args):
 
         def dump_pinned():
             k = eng.particle_num           # the owned set changes as particles migrate
-            return sim.dump_local(out={"position": px[:k], "velocity": pv[:k]})
+            return sim.dump_local(out={"position": px[:k], "velocity": pv[:k]}, color=False)
         state = {"d": dump_pinned()}
         bytes_io = [0, 0]
 

@@ -367,13 +367,17 @@ class ShardedSim:
         """overwrite x, v of this rank's owned particles (order of dump_local) from host arrays"""
         self.engine.upload_xv(pos, vel)
 
-    def dump_local(self, out=None):
+    def dump_local(self, out=None, color=True):
         """this rank's owned particles, in sorted order (keys of dump() + 'orig_id'); `out` may hold
-        preallocated (pinned) arrays for 'position' and 'velocity'"""
+        preallocated (pinned) arrays for 'position' and 'velocity'.  The colour is a host-side
+        function of the original id (a sharded engine does not carry it); color=False skips it."""
         e, out = self.engine, out or {}
         ids = e.download(K.F_ORIG_ID)
-        return {"position": e.download(K.F_X, out.get("position")), "velocity": e.download(K.F_V, out.get("velocity")),
-                "material": e.download(K.F_MATERIAL), "color": self.parts.color_of(ids), "orig_id": ids}
+        d = {"position": e.download(K.F_X, out.get("position")), "velocity": e.download(K.F_V, out.get("velocity")),
+             "material": e.download(K.F_MATERIAL), "orig_id": ids}
+        if color:
+            d["color"] = self.parts.color_of(ids)
+        return d
 
     def dump(self):
         """ParticleSystemV4.dump() of the whole simulation on every rank: the ranks' owned
