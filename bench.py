@@ -328,10 +328,12 @@ def run_gpu(args):
         sim.restore_state()
         rows = int(1.25 * eng.particle_num) + 4096
         px, pv = pinned((rows, 3), np.float32), pinned((rows, 3), np.float32)
+        pm, pid = pinned((rows,), np.int32), pinned((rows,), np.int32)
 
         def dump_pinned():
             k = eng.particle_num           # the owned set changes as particles migrate
-            return sim.dump_local(out={"position": px[:k], "velocity": pv[:k]}, color=False)
+            return sim.dump_local(out={"position": px[:k], "velocity": pv[:k], "material": pm[:k], "orig_id": pid[:k]},
+                                  color=False)
         state = {"d": dump_pinned()}
         bytes_io = [0, 0]
 

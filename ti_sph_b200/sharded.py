@@ -369,12 +369,12 @@ class ShardedSim:
 
     def dump_local(self, out=None, color=True):
         """this rank's owned particles, in sorted order (keys of dump() + 'orig_id'); `out` may hold
-        preallocated (pinned) arrays for 'position' and 'velocity'.  The colour is a host-side
+        preallocated (pinned) arrays for 'position', 'velocity', 'material', 'orig_id'.  The colour is a host-side
         function of the original id (a sharded engine does not carry it); color=False skips it."""
         e, out = self.engine, out or {}
-        ids = e.download(K.F_ORIG_ID)
+        ids = e.download(K.F_ORIG_ID, out.get("orig_id"))
         d = {"position": e.download(K.F_X, out.get("position")), "velocity": e.download(K.F_V, out.get("velocity")),
-             "material": e.download(K.F_MATERIAL), "orig_id": ids}
+             "material": e.download(K.F_MATERIAL, out.get("material")), "orig_id": ids}
         if color:
             d["color"] = self.parts.color_of(ids)
         return d
