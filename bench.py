@@ -396,7 +396,7 @@ def run_gpu(args):
     }
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        leg = cpu_leg(args.workload, args.mode, 1, 1, args.cpu_particles)
+        leg = cpu_leg(args.workload, args.mode, 5, 1, args.cpu_particles)     # ~10 s of CPU work
         cpu = {k: leg[k] for k in ("value", "unit", "cores", "kind", "sample")}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -430,8 +430,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--pre-steps", type=int, default=10, help="steps from the lattice before the state is saved")
     ap.add_argument("--chain", type=int, default=5, help="steps per replay chain (main_3d.py renders every 5)")
-    ap.add_argument("--cpu-particles", type=int, default=500000, help="size of the cpu_baseline sample")
-    ap.add_argument("--ref-particles", type=int, default=250000, help="sample size of --impl reference")
+    ap.add_argument("--cpu-particles", type=int, default=1000000, help="size of the cpu_baseline sample")
+    ap.add_argument("--ref-particles", type=int, default=1000000, help="sample size of --impl reference")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3:
