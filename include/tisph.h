@@ -192,6 +192,11 @@ int tisph_stage_times(tisph_ctx *ctx, int32_t enable, float *ms_update, float *m
  * message buffer. */
 int tisph_shard_config(tisph_ctx *ctx, int32_t plane_lo, int32_t plane_hi, int32_t ghost_planes,
                        int32_t left_lo, int32_t right_hi, int32_t message_capacity);
+/* tisph_shard_config may be called again between steps to move the slab faces (re-balancing): all
+ * ranks must switch at the same step; particles outside the new planes migrate with the next pack. */
+/* Particles per x-plane (gx values) as of the last completed step, ghosts included: a rank reads
+ * its own planes [plane_lo, plane_hi) from it to feed the global histogram that places the faces. */
+int tisph_plane_counts(tisph_ctx *ctx, int32_t *counts);
 /* Fill the two send buffers from the owned particles: every particle within ghost_planes of a
  * slab face, or beyond it (a migrant), goes to that neighbour.  Synchronous; returns counts. */
 int tisph_shard_pack(tisph_ctx *ctx, int32_t *n_left, int32_t *n_right);

@@ -111,6 +111,10 @@ class FakeShardEngine:
         blank["rigidBodies"] = []
         return Gen2Oracle(blank, density_mode=mode, volume_mode=vmode)
 
+    def plane_counts(self):
+        cx = (self.x[:, 0] / self.h).astype(np.int32)
+        return np.bincount(cx, minlength=int(self.config.grid_num[0])).astype(np.int32)
+
     def download(self, field, out=None):
         return {K.F_X: self.x, K.F_V: self.v, K.F_MATERIAL: self.material, K.F_ORIG_ID: self.orig,
                 K.F_DENSITY: self.density, K.F_PRESSURE: self.pressure}[field].copy()

@@ -67,16 +67,18 @@ def _scene():
                        domain_end=(1.0, 1.0, 1.0))
 
 
-def _worker(rank, world, port, mode, steps, outdir):
+def _worker(rank, world, port, mode, steps, outdir, edges=None, rebalance_at=None):
     sys.path.insert(0, HERE)
     from fake_shard_engine import FakeShardEngine
     dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
     scene = _scene()
     sim = ShardedSim(scene, rank, world, comm=TorchDistComm(device="cpu"), density_mode=mode,
-                     engine_factory=lambda cfg: FakeShardEngine(cfg, scene), edges=None)
+                     engine_factory=lambda cfg: FakeShardEngine(cfg, scene), edges=edges)
     owned = [sim.engine.particle_num]
     dumps = []
-    for _ in range(steps):
+    for st in range(steps):
+        if rebalance_at is not None and st == rebalance_at:
+            sim.rebalance()
         sim.step()
         owned.append(sim.engine.particle_num)
         dumps.append(sim.dump())
@@ -113,3 +115,27 @@ def test_sharded_gloo_run_matches_the_global_oracle(world, mode):
             sel = inv[ids]
             assert np.allclose(out[f"position{s}"], ora.x[sel], rtol=0, atol=2e-6)
             assert np.allclose(out[f"velocity{s}"], ora.v[sel], rtol=2e-5, atol=2e-4)
+
+
+def test_rebalancing_moves_the_faces_and_loses_nobody():
+    """start from deliberately lopsided slabs, re-balance after two steps: the faces move towards
+    equal loads (at most to a neighbouring old face per call), results still match the oracle"""
+    steps, world = 5, 3
+    bad_edges = [0, 8, 11, 25]                 # the block spans planes 7..10: rank 0 gets 1/4, rank 2 nothing
+    with tempfile.TemporaryDirectory() as tmp:
+        mp.spawn(_worker, args=(world, _free_port(), "reference", steps, tmp, bad_edges, 2), nprocs=world, join=True)
+        out = np.load(os.path.join(tmp, "out.npz"))
+        owned = [np.load(os.path.join(tmp, f"owned{r}.npy")) for r in range(world)]
+    assert list(out["edges"]) != bad_edges
+    ora = Gen2Oracle(_scene())
+    n = ora.n
+    assert all(sum(o[s] for o in owned) == n for s in range(steps + 1))
+    before = max(o[2] for o in owned) / (n / world)
+    after = max(o[-1] for o in owned) / (n / world)
+    assert after < before                                         # better balanced than before
+    for s in range(steps):
+        ora.step()
+        ids = out[f"orig_id{s}"]
+        assert np.array_equal(np.sort(ids), np.arange(n))
+        inv = np.empty(n, np.int64); inv[ora.orig] = np.arange(n)
+        assert np.allclose(out[f"position{s}"], ora.x[inv[ids]], rtol=0, atol=2e-6)

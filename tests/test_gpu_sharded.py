@@ -131,3 +131,29 @@ def test_local_cluster_one_million_particles():
     assert all(int(s.engine.get_param(K.P_STAT_FALLBACK_FORCE)) == 0 for s in cl.sims)
     for s in cl.sims:
         s.engine.sync(); s.engine.close()
+
+
+def test_local_cluster_rebalancing():
+    """lopsided slabs, re-balanced after two steps (tisph_plane_counts + re-issued
+    tisph_shard_config): faces move, nobody is lost, results still follow the oracle"""
+    bad_edges = [0, 8, 11, 25]
+    cl = LocalCluster(_scene(), 3, edges=bad_edges)
+    ora = Gen2Oracle(_scene())
+    n = ora.n
+    loads = []
+    for s in range(5):
+        if s == 2:
+            new = cl.rebalance()
+            assert new != bad_edges and all(b - a >= 3 for a, b in zip(new, new[1:]))
+        ora.step(); cl.step(1)
+        d = cl.dump()
+        ids = d["orig_id"]
+        assert np.array_equal(np.sort(ids), np.arange(n))
+        inv = np.empty(n, np.int64); inv[ora.orig] = np.arange(n)
+        assert rel_err(d["position"], ora.x[inv[ids]], floor=0.04) < 50 * RTOL
+        loads.append(max(sim.engine.particle_num for sim in cl.sims))
+    assert loads[-1] < loads[1]
+    hist = sum(sim.owned_plane_counts() for sim in cl.sims)
+    assert hist.sum() == n
+    for sim in cl.sims:
+        sim.engine.sync(); sim.engine.close()

@@ -72,6 +72,7 @@ SYMBOLS = {
     "tisph_shard_pack": (C.c_int, [_vp, _ip, _ip]),
     "tisph_shard_buffer": (C.c_int, [_vp, _i32, C.POINTER(_vp), _ip]),
     "tisph_shard_append": (C.c_int, [_vp, _i32, _i32]),
+    "tisph_plane_counts": (C.c_int, [_vp, _vp]),
     "tisph_voxelize_mesh": (C.c_int, [_i32, _vp, _i32, _vp, _i32, C.c_float, _i32, _vp, _vp, _vp]),
 }
 

@@ -768,7 +768,10 @@ int tisph_stage_times(tisph_ctx* c, int32_t enable, float* ms_update, float* ms_
 int tisph_shard_config(tisph_ctx* c, int32_t plane_lo, int32_t plane_hi, int32_t ghost_planes,
                        int32_t left_lo, int32_t right_hi, int32_t message_capacity) {
     CHECK_CTX(c);
-    if (c->have_sorted || c->appended) return fail(TISPH_ERR_INVALID, "configure the slab before the first step");
+    if (c->phase != 0 || c->appended) return fail(TISPH_ERR_INVALID, "slabs can only be (re)configured between steps");
+    if (!c->sharded && c->have_sorted) return fail(TISPH_ERR_INVALID, "turn sharding on before the first step");
+    const bool reconfig = c->sharded;           // moving the slab faces: the particles that fall outside the new
+                                                // planes leave with the next pack, like any other migrant
     if (plane_lo < 0 || plane_hi > c->sp.gx || plane_lo >= plane_hi || ghost_planes < 1 || ghost_planes > 2 ||
         message_capacity <= 0 || left_lo >= plane_lo || (right_hi >= 0 && right_hi <= plane_hi))
         return fail(TISPH_ERR_INVALID, "bad slab [%d,%d) / ghost %d / capacity %d", plane_lo, plane_hi,
@@ -786,7 +789,23 @@ int tisph_shard_config(tisph_ctx* c, int32_t plane_lo, int32_t plane_hi, int32_t
         for (int k = 0; k < 4; ++k) CU(dalloc(&c->msg[k], (size_t)message_capacity * SHARD_REC_F4));
         c->msg_cap = message_capacity;
     }
+    if (reconfig && c->have_sorted) return TISPH_OK;     // the owned slice of the sorted arrays stays what it is
     return set_owned_all(c);
+}
+
+int tisph_plane_counts(tisph_ctx* c, int32_t* counts) {
+    CHECK_CTX(c);
+    if (!counts) return fail(TISPH_ERR_INVALID, "null argument");
+    if (c->cfg.generation != 2) return fail(TISPH_ERR_INVALID, "x-planes exist in the 3D path only");
+    if (!c->have_sorted || c->phase != 0) return fail(TISPH_ERR_INVALID, "plane counts are those of the last completed step");
+    // particles per x-plane at the last sort = differences of the inclusive scan at the plane ends
+    const int gx = c->sp.gx, plane = c->sp.gy * c->sp.gz;
+    std::vector<int> ends((size_t)gx);
+    CU(cudaMemcpy2DAsync(ends.data(), sizeof(int), c->cell_end + (plane - 1), (size_t)plane * sizeof(int), sizeof(int),
+                         (size_t)gx, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    for (int p = 0; p < gx; ++p) counts[p] = ends[p] - (p ? ends[p - 1] : 0);
+    return TISPH_OK;
 }
 
 int tisph_shard_pack(tisph_ctx* c, int32_t* n_left, int32_t* n_right) {

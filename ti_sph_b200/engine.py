@@ -150,6 +150,12 @@ class Engine:
                                            int(left_lo), int(right_hi), int(message_capacity)))
         self._msg_cap = int(message_capacity)
 
+    def plane_counts(self):
+        """particles per x-plane at the last sort (ghosts included)"""
+        out = np.zeros(int(self.config.grid_num[0]), np.int32)
+        check(self._lib.tisph_plane_counts(self._ctx, _ptr(out)))
+        return out
+
     def shard_pack(self):
         nl, nr = C.c_int32(), C.c_int32()
         check(self._lib.tisph_shard_pack(self._ctx, C.byref(nl), C.byref(nr)))

@@ -280,6 +280,7 @@ class ShardedSim:
         for id0, pos, vel, dens, mat in chunks:
             eng.set_param(K.P_ID_BASE, id0)
             eng.add_particles(pos, vel, dens, np.zeros(len(pos), np.float32), mat)
+        self._message_capacity = message_capacity
         self.global_particle_num = self.parts.total
         self.initial_owned = n_own
         self._counts_dev = None
@@ -356,6 +357,41 @@ class ShardedSim:
             for k, v in (("pack", t1 - t0), ("exchange", t2 - t1), ("compute_issue", t3 - t2), ("steps", 1)):
                 self.profile[k] = self.profile.get(k, 0.0) + v
 
+    # -- re-balancing --------------------------------------------------------------------------
+    def owned_plane_counts(self):
+        """this rank's contribution to the global per-plane histogram (its own planes only)"""
+        counts = np.asarray(self.engine.plane_counts(), np.int64)
+        mine = np.zeros_like(counts)
+        mine[self.plane_lo:self.plane_hi] = counts[self.plane_lo:self.plane_hi]
+        return mine
+
+    def apply_histogram(self, plane_counts):
+        """Move the slab faces to where `plane_counts` (global, identical on all ranks) says the
+        load is balanced.  A face moves at most to the old position of a neighbouring face, so
+        that every particle's new owner is the old owner or one of its neighbours and the next
+        pack can carry it there.  Must be called by all ranks between the same two steps."""
+        old = self.edges
+        want = plan_slabs(plane_counts, self.world)
+        new = [0]
+        for k in range(1, self.world):
+            e = min(max(want[k], old[k - 1]), old[k + 1])
+            e = max(e, new[-1] + 3)
+            e = min(e, old[-1] - 3 * (self.world - k))
+            new.append(int(e))
+        new.append(old[-1])
+        self.edges = new
+        r = self.rank
+        self.plane_lo, self.plane_hi = new[r], new[r + 1]
+        self.engine.shard_config(self.plane_lo, self.plane_hi, self.ghost,
+                                 new[r - 1] if self.has_left else -1, new[r + 2] if self.has_right else -1,
+                                 self._message_capacity)
+        return new
+
+    def rebalance(self):
+        """collective: gather the histogram, move the faces (see apply_histogram)"""
+        total = sum(self.comm.all_gather_objects(self.owned_plane_counts()))
+        return self.apply_histogram(total)
+
     # -- state -------------------------------------------------------------------------------
     def save_state(self):
         self.engine.save_state()
@@ -412,6 +448,10 @@ class LocalCluster:
                 sync()
             for s in sims:
                 s.compute()
+
+    def rebalance(self):
+        total = sum(s.owned_plane_counts() for s in self.sims)
+        return [s.apply_histogram(total) for s in self.sims][0]
 
     def dump(self):
         parts = [s.dump_local() for s in self.sims]
