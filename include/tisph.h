@@ -119,7 +119,11 @@ typedef enum tisph_param {
     /* read-only statistics of the last step (tisph_get_param synchronises the stream) */
     TISPH_P_STAT_ITEMS = 7,             /* work items (<= 64 targets of one occupied cell) */
     TISPH_P_STAT_FALLBACK_DENSITY = 8,  /* items whose candidate tile did not fit shared memory */
-    TISPH_P_STAT_FALLBACK_FORCE = 9     /* ... plus items whose neighbour lists overflowed */
+    TISPH_P_STAT_FALLBACK_FORCE = 9,    /* ... plus items whose neighbour lists overflowed */
+    TISPH_P_CFL = 10          /* extension: > 0 turns on a CFL step,
+                                 dt = min(TISPH_P_DT, cfl * h / (c_s + max|v|)), evaluated before every step of
+                                 tisph_step; 0 (default) = the reference's fixed dt.  In a sharded run the
+                                 ranks must agree on dt themselves (ShardedSim does not turn this on). */
 } tisph_param;
 
 const char *tisph_last_error(void);

@@ -114,3 +114,21 @@ def test_gen1_capacity_is_two_to_the_fifteen():
     with pytest.raises(AssertionError):                                          # partice_system.py:150
         ps.add_cube(lower_corner=[1, 1], cube_size=[8.0, 8.0], material=1)
     ps.engine.close()
+
+
+def test_cfl_time_step_extension():
+    """TISPH_P_CFL (extension): dt = min(dt_max, cfl h / (c_s + max|v|)) before every step"""
+    from oracle.oracle import Gen2Oracle
+    scene = small_scene(end=(0.4, 0.2, 0.8))                        # v0 = (0,-1,10): |v| = 10.05
+    ora, eng = make_pair(scene)
+    eng.set_param(K.P_CFL, 0.4)
+    eng.step(1)
+    dt = eng.get_param(K.P_DT)
+    expect = 0.4 * np.float32(0.04) / (np.float32(88.5) + np.sqrt(np.float32(101.0)))
+    assert dt == pytest.approx(float(expect), rel=1e-6) and dt < 2e-4
+    ora.cfg.dt = dt
+    ora.step()
+    assert np.abs(eng.download(K.F_X) - ora.x).max() < 1e-6
+    eng.set_param(K.P_CFL, 0.0)                                     # back to the reference's fixed step
+    assert eng.get_param(K.P_DT) == pytest.approx(2e-4)
+    eng.close()

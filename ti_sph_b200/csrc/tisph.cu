@@ -79,7 +79,8 @@ struct tisph_ctx {
     int diagnostics = 0;
     int variant = 0;
     bool has_boundary = false;
-    int *nbr = nullptr, *nbr_num = nullptr;     // gen-1: particle_neighbors[cap][100], particle_neighbors_num         // any non-fluid particle ever added / announced (TISPH_P_HAS_BOUNDARY)
+    int *nbr = nullptr, *nbr_num = nullptr;     // gen-1: particle_neighbors[cap][100], particle_neighbors_num
+    float cfl = 0.f;                            // > 0: dt = min(cfg.dt, cfl * h / (c_s + max|v|)) before every step         // any non-fluid particle ever added / announced (TISPH_P_HAS_BOUNDARY)
     // slab sharding (tisph_shard.cuh)
     int *rank_key = nullptr;
     bool sharded = false;
@@ -545,6 +546,23 @@ int tisph_step(tisph_ctx* c, int32_t nsteps) {
     for (int s = 0; s < nsteps; ++s) {
         bool t = c->timing && c->timed < MAX_TIMED_STEPS;
         int rc;
+        if (c->cfl > 0.f && !c->appended) {     // optional CFL step (extension): one small reduction + one sync per step
+            if ((rc = ensure_range(c))) return rc;
+            unsigned int bits = 0u;
+            unsigned int* d = (unsigned int*)(c->err_dev + 2);
+            int n_own = c->o_hi - c->o_lo;
+            CU(cudaMemsetAsync(d, 0, 4, c->stream));
+            if (n_own > 0)
+                k_vmax<<<nblocks(n_own, 256) < 1184 ? nblocks(n_own, 256) : 1184, 256, 0, c->stream>>>(
+                    n_own, c->V[c->cur] + c->o_lo, c->Q[c->cur] + c->o_lo, d);
+            c->launches += 1;
+            CU(cudaMemcpyAsync(&bits, d, 4, cudaMemcpyDeviceToHost, c->stream));
+            CU(cudaStreamSynchronize(c->stream));
+            float v2;
+            memcpy(&v2, &bits, 4);
+            float dt = c->cfl * c->cfg.support / (c->cfg.c_s + sqrtf(v2));
+            c->sp.dt = dt < c->cfg.dt ? dt : c->cfg.dt;
+        }
         if (t) CU(cudaEventRecord(c->ev[c->timed][0], c->stream));
         if ((rc = run_update(c))) return rc;
         if (t) CU(cudaEventRecord(c->ev[c->timed][1], c->stream));
@@ -686,6 +704,7 @@ int tisph_set_param(tisph_ctx* c, int32_t param, double value) {
     CHECK_CTX(c);
     switch (param) {
         case TISPH_P_DT: c->cfg.dt = (float)value; c->sp.dt = (float)value; return TISPH_OK;
+        case TISPH_P_CFL: c->cfl = (float)value; if (c->cfl <= 0.f) c->sp.dt = c->cfg.dt; return TISPH_OK;
         case TISPH_P_DENSITY_MODE: c->cfg.density_mode = (int)value; c->sp.density_mode = (int)value; return TISPH_OK;
         case TISPH_P_VOLUME_MODE: c->cfg.volume_mode = (int)value; c->sp.volume_mode = (int)value; return TISPH_OK;
         case TISPH_P_DIAGNOSTICS:
@@ -707,7 +726,8 @@ int tisph_set_param(tisph_ctx* c, int32_t param, double value) {
 int tisph_get_param(tisph_ctx* c, int32_t param, double* value) {
     if (!c || !value) return fail(TISPH_ERR_INVALID, "null argument");
     switch (param) {
-        case TISPH_P_DT: *value = c->cfg.dt; return TISPH_OK;
+        case TISPH_P_DT: *value = c->sp.dt; return TISPH_OK;      // the dt of the last step when TISPH_P_CFL is on
+        case TISPH_P_CFL: *value = c->cfl; return TISPH_OK;
         case TISPH_P_DENSITY_MODE: *value = c->cfg.density_mode; return TISPH_OK;
         case TISPH_P_VOLUME_MODE: *value = c->cfg.volume_mode; return TISPH_OK;
         case TISPH_P_DIAGNOSTICS: *value = c->diagnostics; return TISPH_OK;

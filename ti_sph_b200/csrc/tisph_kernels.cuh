@@ -296,6 +296,20 @@ k_unpack(int n, const float4* __restrict__ src, int comp0, int ncomp, uint32_t* 
     for (int k = 0; k < ncomp; ++k) dst[(size_t)i * ncomp + k] = w[comp0 + k];
 }
 
+// max |v|^2 over the fluid particles, as float bits (non-negative floats order like unsigned ints):
+// input of the optional CFL time step (an extension; the reference's dt is fixed, sph_basev2.py:14-15)
+__global__ void __launch_bounds__(256)
+k_vmax(int n, const float4* __restrict__ V, const float4* __restrict__ Q, unsigned int* __restrict__ out) {
+    unsigned int m = 0u;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        if (__float_as_int(Q[i].z) != MAT_FLUID) continue;
+        float4 v = V[i];
+        m = max(m, __float_as_uint(v.x * v.x + v.y * v.y + v.z * v.z));
+    }
+    m = __reduce_max_sync(0xffffffffu, m);
+    if ((threadIdx.x & 31) == 0 && m > 0u) atomicMax(out, m);
+}
+
 // colour is kept in insertion order and gathered through orig_id at dump time
 __global__ void __launch_bounds__(256)
 k_gather_color(int n, int ncomp, const float4* __restrict__ Q, const int* __restrict__ color,
