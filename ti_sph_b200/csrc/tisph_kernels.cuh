@@ -1,4 +1,5 @@
-// tisph_kernels.cuh -- the sm_100a kernels of the WCSPH step.
+// tisph_kernels.cuh -- binning / scan / sort kernels and layout conversion of the WCSPH step
+// (the neighbour walks are in tisph_walk.cuh, gen-1 in tisph_gen1.cuh, sharding in tisph_shard.cuh).
 //
 // Data layout in HBM (all arrays float4 / 16-byte records, capacity-sized, two copies
 // "cur" and "other" that ping-pong inside a step):
@@ -197,16 +198,11 @@ k_reorder(int n, const int* __restrict__ keys, const int* __restrict__ ids,
 }
 
 // ---------------------------------------------------------------------------------------
-// Neighbour walks.  One CTA per cell.  The 27 neighbour cells are 9 contiguous ranges of the
-// sorted arrays (z is the fastest key digit, so cells (x,y,cz-1..cz+1) are adjacent); they
-// are staged into shared memory tile by tile and every thread walks them as broadcast
-// reads.  The CTA's threads are arranged as  [split][target lane]: 32 or 64 target particles
-// of the cell, each walked by 8 or 4 "split" threads that take interleaved 32-candidate
-// chunks; partial sums are combined through shared memory.
-//
-// Candidate range of cell c is [cell_end[max(0,c-1)], cell_end[c])  (partice_systemv4.py:343),
-// which makes cell 0 invisible as a neighbour (reference quirk, reproduced). Cells outside
-// the grid are empty (the reference reads out of bounds there).
+// Geometry shared by the neighbour walks (tisph_walk.cuh).  The 27 neighbour cells of a cell are 9
+// contiguous ranges of the sorted arrays (z is the fastest key digit, so cells (x,y,cz-1..cz+1)
+// are adjacent).  Candidate range of cell c is [cell_end[max(0,c-1)], cell_end[c])
+// (partice_systemv4.py:343), which makes cell 0 invisible as a neighbour (reference quirk,
+// reproduced).  Cells outside the grid are empty (the reference reads out of bounds there).
 // ---------------------------------------------------------------------------------------
 constexpr int NB_THREADS = 256;
 

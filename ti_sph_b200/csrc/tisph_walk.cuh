@@ -1,27 +1,32 @@
 // tisph_walk.cuh -- the two neighbour walks of a WCSPH step on sm_100a.
 //
 // Work items.  A walk is cut into ITEMS: one item = up to 64 target particles of one occupied
-// grid cell (k_items builds the list after the scan).  Persistent CTAs of 256 threads pull items
-// from an atomic counter, so the 97 % empty cells of a dam-break grid cost nothing.  Inside an
-// item the CTA's threads are arranged [split][target lane]: 32 or 64 targets, each walked by 8 or
-// 4 "split" threads that take interleaved 32-candidate chunks of the item's candidate tile; the
-// partial sums meet in shared memory.
+// grid cell, 32 where the 27-cell neighbourhood is dense (k_items builds the list after the scan).
+// Persistent CTAs of 256 threads pull items from an atomic cursor, so the ~97 % empty cells of a
+// dam-break grid cost nothing.  Inside an item the CTA's threads are arranged [split][target
+// lane]: 64 (32) targets, each walked by 4 (8) "split" threads; split s takes the candidate PAIRS
+// s, s + nsplit, ... (pair-wise interleave keeps the splits' survivor counts balanced on
+// lattice-like states); the partial sums meet in shared memory.
 //
 // Candidate tile.  The 27 neighbour cells of a cell are 9 contiguous ranges of the sorted arrays
-// (z is the fastest key digit), staged into shared memory once per item.  Range of cell c is
+// (z is the fastest key digit); they are staged into shared memory TCAP candidates at a time (one
+// tile at the reference spacing, several where cells are crowded).  Range of cell c is
 // [cell_end[max(0,c-1)], cell_end[c])  (partice_systemv4.py:343; cell 0 is therefore invisible as
 // a neighbour -- reference quirk, reproduced).  Cells outside the grid are empty (the reference
-// reads out of bounds there).
+// reads out of bounds there).  In shared memory the pairs of one split are contiguous (pair_slot),
+// so the filter reads consecutive slots and the random gathers of a warp spread over all banks.
 //
 // Walk 1 (k_density_list): FILTER every candidate with packed f32x2 arithmetic (FADD2 / FMUL2 /
-// FFMA2: two candidates per instruction) against a cutoff widened by 1e-6 -- a superset of the
-// neighbours -- appending survivors to a per-thread pending list in shared memory ([slot][thread],
-// conflict free); DRAIN the lists on nearly full warps: exact IEEE test sqrt(d2) < h in the
-// reference's evaluation order (bit-exact neighbour set), kernel sum, count.  The drained lists
-// are also streamed to global memory (u16 tile indices, 4 per 8-byte word, [word][thread]).
-// Walk 2 (k_force_list): no filter at all -- every thread replays its list from global memory and
-// evaluates the pair forces; then advect + walls.  Items whose tile or list does not fit go
-// through the self-contained fallback kernels (k_density_fb / k_force_fb) instead.
+// FFMA2: two candidates per instruction, broadcast loads) against a cutoff widened by 1e-6 -- a
+// superset of the neighbours -- pushing the survivors' slots to a per-thread pending list in shared
+// memory ([slot][thread]); DRAIN the lists in words of four entries, branch-free: exact IEEE
+// test sqrt(d2) < h in the reference's evaluation order (bit-exact neighbour count), kernel sum.
+// The drained entries ((tile << 11) | slot, u16, 4 per 8-byte word, [word][thread]) are streamed
+// to the item's rows of the global neighbour-list pool.
+// Walk 2 (k_force_list): no filter at all -- every thread replays its list and evaluates the
+// pair forces branch-free; then advect + walls.  Items that the list path cannot take (more than
+// MAX_TOTAL candidates, a list longer than its reservation, pool exhausted) go through the
+// self-contained fallback kernels (k_density_fb / k_force_fb); none do in the benchmarks.
 #pragma once
 #include "tisph_device.cuh"
 
