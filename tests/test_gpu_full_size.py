@@ -96,3 +96,72 @@ def test_c5_sixteen_million_particles_properties():
     assert np.array_equal(out1[0], out2[0]) and np.array_equal(out1[1], out2[1])
     assert int(eng.get_param(K.P_STAT_FALLBACK_FORCE)) == 0
     eng.sync(); eng.close()
+
+
+def test_c2_shipped_demo_3d_scene_against_the_oracle_and_survey_values():
+    """BASELINE config C2 = data/scenes/demo_3d.json as shipped (195,300 particles) through the
+    drop-in classes; SURVEY section 4 known-answer values on the GPU result"""
+    import json
+    import os
+    from core.partice_system.partice_systemv4 import ParticleSystemV4
+    from core.sph.wcsphv2 import WCSPHV2
+    from oracle.oracle import Gen2Oracle
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    with open(os.path.join(root, "data", "scenes", "demo_3d.json")) as f:
+        scene = json.load(f)
+    ps = ParticleSystemV4(scene)
+    solver = WCSPHV2(ps)
+    eng = ps.engine
+    assert ps.particle_num[None] == 195300 and list(ps.grid_num) == [125, 75, 50]
+    ora = Gen2Oracle(scene)
+    t = ora.step(trace=True)
+    solver.step()
+    ids = eng.download(K.F_ORIG_ID)
+    assert np.array_equal(ids, t["orig"])
+    nc = eng.download(K.F_NEIGHBOR_COUNT)
+    assert np.array_equal(nc, t["neighbor_count"]) and (nc.min(), nc.max(), int(nc.sum())) == (50, 255, 45273868)
+    inv = np.empty(len(ids), np.int64); inv[ids] = np.arange(len(ids))
+    S, a = eng.download(K.F_DENSITY_SUM), eng.download(K.F_D_VELOCITY)
+    for idx, nn, s_ref, dv in [(0, 51, 1703.690, (19.0562, 9.2462, 19.0562)),
+                               (99060, 253, 6145.846, (-1.0e-4, -9.80986, 1.0e-4)),
+                               (1410, 150, 4065.557, (41.2480, -9.80990, 7.0e-5))]:
+        s = inv[idx]
+        assert nc[s] == nn and S[s] == pytest.approx(s_ref, rel=5e-6)
+        assert np.allclose(a[s], dv, rtol=2e-5, atol=3e-5)
+    d = ps.dump()
+    assert rel_err(d["position"], ora.x, floor=0.04) < RTOL
+    assert np.array_equal(d["material"], ora.material) and np.array_equal(d["color"], ora.color)
+    eng.close()
+
+
+def test_c4_four_million_particles_with_a_mesh_sampled_boundary():
+    """BASELINE config C4: 200 x 200 x 100 fluid block (r = 0.005) over a voxelised 50,000-triangle
+    mesh (the reference's Dragon_50k.obj if it has been put under data/models, else a procedural
+    torus), one step against the oracle fed with the same boundary points"""
+    import sys
+    import os
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from bench import workload_scene
+    from core.partice_system.partice_systemv4 import ParticleSystemV4
+    from core.sph.wcsphv2 import WCSPHV2
+    from oracle.oracle import Gen2Oracle
+    scene = workload_scene("C4")
+    ps = ParticleSystemV4(scene, volume_mode="akinci")
+    solver = WCSPHV2(ps)
+    eng = ps.engine
+    pts = ps.rigidBodiesConfig[0]["voxelized_points"]
+    n = ps.particle_num[None]
+    assert n == 4_000_000 + len(pts) and len(pts) > 50_000
+    bare = dict(scene, rigidBodies=[dict(scene["rigidBodies"][0])])
+    ora = Gen2Oracle(bare, volume_mode="akinci", boundary_points=pts)
+    assert ora.n == n
+    ora.step()
+    solver.step()
+    d = ps.dump()
+    assert np.array_equal(eng.download(K.F_ORIG_ID), ora.orig)
+    assert np.array_equal(d["material"], ora.material)
+    assert rel_err(d["position"], ora.x, floor=0.02) < RTOL
+    assert rel_err(ps.volume.to_numpy(), ora.volume) < RTOL
+    assert vec_rel_err(d["velocity"], ora.v, floor=1.0) < 5 * RTOL
+    assert int(eng.get_param(K.P_STAT_FALLBACK_FORCE)) == 0
+    eng.close()
