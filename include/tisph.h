@@ -206,6 +206,14 @@ int tisph_plane_counts(tisph_ctx *ctx, int32_t *counts);
 int tisph_shard_pack(tisph_ctx *ctx, int32_t *n_left, int32_t *n_right);
 /* Device pointer of a message buffer: 0 send-left, 1 send-right, 2 recv-left, 3 recv-right. */
 int tisph_shard_buffer(tisph_ctx *ctx, int32_t which, void **ptr, int32_t *capacity_records);
+/* Peer-to-peer halo (optional, one node): every rank exports CUDA IPC handles of its four receive
+ * buffers (two per side, used alternately) and connects to those of its neighbours; from then on
+ * tisph_shard_pack writes the records straight into the neighbour's receive buffer over NVLink and
+ * only the two counts have to be exchanged by the host.  handles: 4 cudaIpcMemHandle_t (256 bytes). */
+int tisph_shard_ipc_export(tisph_ctx *ctx, void *handles, size_t bytes);
+int tisph_shard_ipc_connect(tisph_ctx *ctx, int32_t side /* 0 left, 1 right */, const void *handles, size_t bytes);
+/* Back to the local send buffers (all ranks must agree on which path they use). */
+int tisph_shard_ipc_disconnect(tisph_ctx *ctx);
 /* Make the received records part of the particle set of the coming step. */
 int tisph_shard_append(tisph_ctx *ctx, int32_t n_from_left, int32_t n_from_right);
 

@@ -23,6 +23,7 @@ def main():
         sim = ShardedSim(_scene(), rank, world, comm=TorchDistComm(device=f"cuda:{local}"),
                          density_mode=mode, device=local)
         if rank == 0:
+            print("halo path:", "p2p" if sim.p2p else "nccl", flush=True)
             check_against_oracle(lambda: sim.step(1), sim.dump, mode)
         else:
             for _ in range(4):

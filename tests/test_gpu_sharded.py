@@ -70,19 +70,23 @@ def test_local_cluster_save_restore_replays_the_same_steps():
     assert np.array_equal(a["orig_id"], b["orig_id"]) and np.array_equal(a["position"], b["position"])
 
 
-def test_nccl_two_gpus():
+@pytest.mark.parametrize("p2p", ["1", "0"], ids=["p2p-halo", "nccl-halo"])
+def test_two_gpus_over_torchrun(p2p):
+    """one process per GPU: records either written by the pack kernel straight into the neighbour's
+    receive buffer (CUDA IPC over NVLink) or sent with NCCL send/recv"""
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
            "--master-addr", "127.0.0.1", "--master-port", "29611", os.path.join(HERE, "dist_worker.py")]
-    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, TISPH_P2P_HALO=p2p))
     if res.returncode != 0 or "SHARDED-NCCL-OK" not in res.stdout:
         os.makedirs(os.path.join(os.path.dirname(HERE), "gpurun_out"), exist_ok=True)
-        with open(os.path.join(os.path.dirname(HERE), "gpurun_out", "nccl_worker_failure.log"), "w") as fh:
+        with open(os.path.join(os.path.dirname(HERE), "gpurun_out", f"dist_worker_failure_p2p{p2p}.log"), "w") as fh:
             fh.write(res.stdout + "\n----- stderr -----\n" + res.stderr)
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
     assert "SHARDED-NCCL-OK" in res.stdout
+    assert f"halo path: {'p2p' if p2p == '1' else 'nccl'}" in res.stdout
 
 
 @pytest.mark.parametrize("vmode,dmode", [("reference", "reference"), ("akinci", "summed")])

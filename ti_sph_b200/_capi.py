@@ -73,6 +73,9 @@ SYMBOLS = {
     "tisph_shard_buffer": (C.c_int, [_vp, _i32, C.POINTER(_vp), _ip]),
     "tisph_shard_append": (C.c_int, [_vp, _i32, _i32]),
     "tisph_plane_counts": (C.c_int, [_vp, _vp]),
+    "tisph_shard_ipc_export": (C.c_int, [_vp, _vp, C.c_size_t]),
+    "tisph_shard_ipc_connect": (C.c_int, [_vp, _i32, _vp, C.c_size_t]),
+    "tisph_shard_ipc_disconnect": (C.c_int, [_vp]),
     "tisph_voxelize_mesh": (C.c_int, [_i32, _vp, _i32, _vp, _i32, C.c_float, _i32, _vp, _vp, _vp]),
 }
 

@@ -91,7 +91,14 @@ struct tisph_ctx {
     bool range_valid = true;
     int* range_dev = nullptr;          // {o_lo, o_hi} on the device
     ShardCounters* shard_ctr = nullptr;
-    float4* msg[4] = {nullptr, nullptr, nullptr, nullptr};   // send_left, send_right, recv_left, recv_right
+    float4* msg[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+                                       // send_left, send_right, recv_left[0], recv_right[0], recv_left[1], recv_right[1]
+    // peer-to-peer halo: the neighbours' receive buffers (two per side, used alternately), mapped
+    // into this process with CUDA IPC; the pack kernel then writes the records over NVLink itself
+    float4* peer[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};   // [side 0 left / 1 right][parity]
+    void* ipc_opened[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    int n_ipc_opened = 0;
+    unsigned pack_seq = 0;             // packs issued so far; pack k and append k use parity k & 1
     int msg_cap = 0;                   // records per message buffer
     int id_base = 0;                   // original id of the next particle added
     int64_t launches = 0;
@@ -415,7 +422,8 @@ int tisph_destroy(tisph_ctx* c) {
     cudaFree(c->Lg); cudaFree(c->item_row);
     cudaFree(c->rank_key); cudaFree(c->range_dev); cudaFree(c->shard_ctr);
     cudaFree(c->nbr); cudaFree(c->nbr_num);
-    for (int k = 0; k < 4; ++k) cudaFree(c->msg[k]);
+    for (int k = 0; k < 6; ++k) cudaFree(c->msg[k]);
+    for (int k = 0; k < c->n_ipc_opened; ++k) cudaIpcCloseMemHandle(c->ipc_opened[k]);
     if (c->ev_made)
         for (int s = 0; s < MAX_TIMED_STEPS; ++s)
             for (int k = 0; k < 4; ++k) cudaEventDestroy(c->ev[s][k]);
@@ -805,12 +813,48 @@ int tisph_shard_config(tisph_ctx* c, int32_t plane_lo, int32_t plane_hi, int32_t
     c->sp.walk_key_lo = (plane_lo - 1 > 0 ? plane_lo - 1 : 0) * plane;
     c->sp.walk_key_hi = (plane_hi + 1 < c->sp.gx ? plane_hi + 1 : c->sp.gx) * plane;
     if (message_capacity != c->msg_cap) {
-        for (int k = 0; k < 4; ++k) { cudaFree(c->msg[k]); c->msg[k] = nullptr; }
-        for (int k = 0; k < 4; ++k) CU(dalloc(&c->msg[k], (size_t)message_capacity * SHARD_REC_F4));
+        if (c->peer[0][0] || c->peer[1][0])
+            return fail(TISPH_ERR_INVALID, "the message capacity cannot change once peers have mapped the buffers");
+        for (int k = 0; k < 6; ++k) { cudaFree(c->msg[k]); c->msg[k] = nullptr; }
+        for (int k = 0; k < 6; ++k) CU(dalloc(&c->msg[k], (size_t)message_capacity * SHARD_REC_F4));
         c->msg_cap = message_capacity;
     }
     if (reconfig && c->have_sorted) return TISPH_OK;     // the owned slice of the sorted arrays stays what it is
     return set_owned_all(c);
+}
+
+int tisph_shard_ipc_export(tisph_ctx* c, void* handles, size_t bytes) {
+    CHECK_CTX(c);
+    if (!c->sharded || !handles || bytes != 4 * sizeof(cudaIpcMemHandle_t))
+        return fail(TISPH_ERR_INVALID, "needs a sharded context and room for 4 handles of %zu bytes", sizeof(cudaIpcMemHandle_t));
+    cudaIpcMemHandle_t* h = (cudaIpcMemHandle_t*)handles;
+    for (int k = 0; k < 4; ++k) CU(cudaIpcGetMemHandle(&h[k], c->msg[2 + k]));   // recv_left[0], recv_right[0], recv_left[1], recv_right[1]
+    return TISPH_OK;
+}
+
+int tisph_shard_ipc_connect(tisph_ctx* c, int32_t side, const void* handles, size_t bytes) {
+    CHECK_CTX(c);
+    if (!c->sharded || (side != 0 && side != 1) || !handles || bytes != 4 * sizeof(cudaIpcMemHandle_t))
+        return fail(TISPH_ERR_INVALID, "bad argument");
+    if (c->n_ipc_opened + 2 > 8) return fail(TISPH_ERR_INVALID, "peers already connected");
+    const cudaIpcMemHandle_t* h = (const cudaIpcMemHandle_t*)handles;
+    // what I send to my LEFT neighbour it receives from its RIGHT, and vice versa
+    for (int par = 0; par < 2; ++par) {
+        void* p = nullptr;
+        CU(cudaIpcOpenMemHandle(&p, h[2 * par + (side == 0 ? 1 : 0)], cudaIpcMemLazyEnablePeerAccess));
+        c->ipc_opened[c->n_ipc_opened++] = p;
+        c->peer[side][par] = (float4*)p;
+    }
+    return TISPH_OK;
+}
+
+int tisph_shard_ipc_disconnect(tisph_ctx* c) {
+    CHECK_CTX(c);
+    CU(cudaStreamSynchronize(c->stream));
+    for (int k = 0; k < c->n_ipc_opened; ++k) cudaIpcCloseMemHandle(c->ipc_opened[k]);
+    c->n_ipc_opened = 0;
+    for (int sd = 0; sd < 2; ++sd) c->peer[sd][0] = c->peer[sd][1] = nullptr;
+    return TISPH_OK;
 }
 
 int tisph_plane_counts(tisph_ctx* c, int32_t* counts) {
@@ -837,10 +881,13 @@ int tisph_shard_pack(tisph_ctx* c, int32_t* n_left, int32_t* n_right) {
     CU(cudaMemsetAsync(c->shard_ctr, 0, sizeof(ShardCounters), st));
     // the owned slice is read from device memory: no host round trip between the step and the pack
     const int n_upper = c->range_valid ? c->o_hi - c->o_lo : c->n;
+    const int par = (int)(c->pack_seq & 1u);       // which of the neighbour's two receive buffers this step fills
+    c->pack_seq++;
     if (n_upper > 0) {
         k_shard_pack<<<nblocks(n_upper, 256), 256, 0, st>>>(
             c->sp, n_upper, c->range_dev, c->plane_lo, c->plane_hi, c->ghost, c->left_lo, c->right_hi,
-            c->msg_cap, c->P[c->cur], c->V[c->cur], c->Q[c->cur], c->msg[0], c->msg[1], c->shard_ctr);
+            c->msg_cap, c->P[c->cur], c->V[c->cur], c->Q[c->cur],
+            c->peer[0][par] ? c->peer[0][par] : c->msg[0], c->peer[1][par] ? c->peer[1][par] : c->msg[1], c->shard_ctr);
         c->launches += 1;
         CU(cudaGetLastError());
     }
@@ -863,7 +910,9 @@ int tisph_shard_pack(tisph_ctx* c, int32_t* n_left, int32_t* n_right) {
 int tisph_shard_buffer(tisph_ctx* c, int32_t which, void** ptr, int32_t* capacity_records) {
     if (!c || !ptr) return fail(TISPH_ERR_INVALID, "null argument");
     if (!c->sharded || which < 0 || which > 3) return fail(TISPH_ERR_INVALID, "no such message buffer");
-    *ptr = c->msg[which];
+    // the receive buffers alternate with the step: the one the last pack's step uses
+    const int par = c->pack_seq ? (int)((c->pack_seq - 1) & 1u) : 0;
+    *ptr = which < 2 ? c->msg[which] : c->msg[which + 2 * par];
     if (capacity_records) *capacity_records = c->msg_cap;
     return TISPH_OK;
 }
@@ -880,11 +929,12 @@ int tisph_shard_append(tisph_ctx* c, int32_t n_from_left, int32_t n_from_right) 
                     c->o_lo, c->o_hi, n_from_left, n_from_right, c->cap);
     cudaStream_t st = c->stream;
     int cur = c->cur;
+    const int par = c->pack_seq ? (int)((c->pack_seq - 1) & 1u) : 0;
     if (n_from_left > 0)
-        k_shard_append<<<nblocks(n_from_left, 256), 256, 0, st>>>(n_from_left, c->msg[2], c->o_hi, c->P[cur],
+        k_shard_append<<<nblocks(n_from_left, 256), 256, 0, st>>>(n_from_left, c->msg[2 + 2 * par], c->o_hi, c->P[cur],
                                                                   c->V[cur], c->Q[cur]);
     if (n_from_right > 0)
-        k_shard_append<<<nblocks(n_from_right, 256), 256, 0, st>>>(n_from_right, c->msg[3], c->o_hi + n_from_left,
+        k_shard_append<<<nblocks(n_from_right, 256), 256, 0, st>>>(n_from_right, c->msg[3 + 2 * par], c->o_hi + n_from_left,
                                                                    c->P[cur], c->V[cur], c->Q[cur]);
     c->launches += (n_from_left > 0) + (n_from_right > 0);
     CU(cudaGetLastError());

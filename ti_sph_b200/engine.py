@@ -173,6 +173,19 @@ class Engine:
             return torch.empty((0, 12), dtype=torch.float32, device=f"cuda:{self.config.device}")
         return torch.as_tensor(_DeviceArray(p.value, (int(n), 12)), device=f"cuda:{self.config.device}")
 
+    def shard_ipc_export(self):
+        """CUDA IPC handles of this context's four receive buffers (bytes)"""
+        buf = C.create_string_buffer(256)
+        check(self._lib.tisph_shard_ipc_export(self._ctx, buf, 256))
+        return buf.raw
+
+    def shard_ipc_connect(self, side, handles):
+        """map the receive buffers of the neighbour on `side` (0 left, 1 right): packs then write there"""
+        check(self._lib.tisph_shard_ipc_connect(self._ctx, int(side), C.create_string_buffer(handles, 256), 256))
+
+    def shard_ipc_disconnect(self):
+        check(self._lib.tisph_shard_ipc_disconnect(self._ctx))
+
     def shard_append(self, n_from_left, n_from_right):
         check(self._lib.tisph_shard_append(self._ctx, int(n_from_left), int(n_from_right)))
 

@@ -296,6 +296,24 @@ class ShardedSim:
         if comm is not None and world > 1 and os.environ.get("TISPH_SHM_COUNTS", "1") != "0" and \
                 os.environ.get("LOCAL_WORLD_SIZE", str(world)) == str(world):
             self._shm = ShmCounts(comm, rank, world)
+        # Peer-to-peer halo: with every rank on this node and CUDA IPC available, the pack kernel writes
+        # the records straight into the neighbour's receive buffer over NVLink; the host only passes the
+        # two counts (ShmCounts).  All ranks must agree, otherwise everybody stays on NCCL send/recv.
+        self.p2p = False
+        if self._shm is not None and self.stream is not None and engine_factory.__name__ == "Engine" and \
+                os.environ.get("TISPH_P2P_HALO", "1") != "0":
+            handles = comm.all_gather_objects(eng.shard_ipc_export())
+            ok = True
+            try:
+                if self.has_left:
+                    eng.shard_ipc_connect(0, handles[rank - 1])
+                if self.has_right:
+                    eng.shard_ipc_connect(1, handles[rank + 1])
+            except Exception:
+                ok = False
+            self.p2p = all(comm.all_gather_objects(ok))
+            if not self.p2p:
+                eng.shard_ipc_disconnect()
         self.profile = {} if os.environ.get("TISPH_SHARD_PROFILE") else None
 
     # -- the phases of one step (LocalCluster drives them for several ranks in one process) -----
@@ -329,6 +347,9 @@ class ShardedSim:
             ml, mr = rcv.tolist()                  # one synchronisation for both counts
             ml = ml if self.has_left else 0
             mr = mr if self.has_right else 0
+        if self.p2p:                           # the records are already in place (written by the neighbours' packs)
+            self._nrecv = (ml, mr)
+            return self._nrecv
         comm.exchange(self.rank,
                       eng.message_tensor(SEND_LEFT, nl) if self.has_left and nl else None,
                       eng.message_tensor(SEND_RIGHT, nr) if self.has_right and nr else None,
