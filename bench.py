@@ -409,7 +409,10 @@ def run_gpu(args):
                             f"{CHAIN} steps (device-side restore inside the timed region)",
                    "l2": "state (48 B/particle x 2 copies) larger than L2" if n_total * 96 > 126e6
                          else "state fits L2 (small workload)",
-                   "parallelism": "single GPU" if world == 1 else f"x-slabs x{world}, halo exchange over NCCL"},
+                   "parallelism": "single GPU" if world == 1 else
+                   f"x-slabs x{world}, halo records " + ("written by the pack kernel into the neighbour's buffer over NVLink "
+                                                          "(CUDA IPC), counts through shared memory" if sim.p2p
+                                                          else "over NCCL send/recv")},
         "clocks": clk, "gpu_launches": int(launches), "roofline": roofline,
     }
     line["e2e"] = e2e
