@@ -20,7 +20,7 @@ import numpy as np
 from ti_sph_b200 import _capi as K
 from ti_sph_b200 import scene as _scene
 from ti_sph_b200.engine import Engine
-from ti_sph_b200.fields import FieldView, ScalarView
+from ti_sph_b200.fields import ConstantField, FieldView, ScalarView
 
 
 class ParticleSystemV4:
@@ -65,6 +65,7 @@ class ParticleSystemV4:
                           ("grid_ids", K.F_GRID_IDS),
                           ("grid_particles_num", K.F_GRID_PARTICLES_NUM)):
             setattr(self, name, FieldView(self, fid, name))
+        self.m = ConstantField(self, "m")            # allocated, sorted along and never written by the reference (:39)
         self.add_fluid_and_rigid()
         if self.engine.particle_num != self.particle_max_num:
             # reference quirk Q10: its counting pre-pass and add_cube can disagree by round-off;

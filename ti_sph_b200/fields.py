@@ -88,3 +88,27 @@ class ScalarView:
 
     def to_numpy(self):
         return np.asarray(self._get())
+
+
+class ConstantField:
+    """A per-particle field that the reference allocates but never writes (ParticleSystemV4.m,
+    partice_systemv4.py:39): all zeros, nothing is stored for it."""
+
+    def __init__(self, owner, name, dtype=np.float32):
+        self._owner, self.name, self.dtype = owner, name, np.dtype(dtype)
+
+    @property
+    def shape(self):
+        return (self._owner.engine.particle_num,)
+
+    def to_numpy(self):
+        return np.zeros(self.shape, self.dtype)
+
+    def __array__(self, dtype=None, copy=None):
+        return self.to_numpy() if dtype is None else self.to_numpy().astype(dtype)
+
+    def __len__(self):
+        return self.shape[0]
+
+    def __getitem__(self, idx):
+        return self.to_numpy()[idx]
