@@ -124,6 +124,9 @@ typedef enum tisph_param {
                                  dt = min(TISPH_P_DT, cfl * h / (c_s + max|v|)), evaluated before every step of
                                  tisph_step; 0 (default) = the reference's fixed dt.  In a sharded run the
                                  ranks must agree on dt themselves (ShardedSim does not turn this on). */
+    , TISPH_P_STAT_CHECK_FAILURES = 11 /* read-only: device-side bounds checks that failed so far, in libraries
+                                 built with -DTISPH_CHECKS (count + first failing source line / 1e6);
+                                 -1 when the checks are compiled out */
 } tisph_param;
 
 const char *tisph_last_error(void);

@@ -40,7 +40,7 @@ F_X, F_V, F_MASS, F_VOLUME, F_DENSITY, F_PRESSURE, F_MATERIAL, F_COLOR, F_GRID_I
 STAGE_UPDATE, STAGE_DENSITY, STAGE_FORCE_ADVECT = range(3)
 # enum tisph_param
 P_DT, P_DENSITY_MODE, P_VOLUME_MODE, P_DIAGNOSTICS, P_KERNEL_VARIANT, P_ID_BASE, P_HAS_BOUNDARY, \
-    P_STAT_ITEMS, P_STAT_FALLBACK_DENSITY, P_STAT_FALLBACK_FORCE, P_CFL = range(11)
+    P_STAT_ITEMS, P_STAT_FALLBACK_DENSITY, P_STAT_FALLBACK_FORCE, P_CFL, P_STAT_CHECK_FAILURES = range(12)
 
 ERR_NO_DEVICE = -5
 

@@ -736,6 +736,18 @@ int tisph_get_param(tisph_ctx* c, int32_t param, double* value) {
     switch (param) {
         case TISPH_P_DT: *value = c->sp.dt; return TISPH_OK;      // the dt of the last step when TISPH_P_CFL is on
         case TISPH_P_CFL: *value = c->cfl; return TISPH_OK;
+        case TISPH_P_STAT_CHECK_FAILURES: {      // debug builds (-DTISPH_CHECKS): failed device-side bounds checks
+            int h[2] = {0, 0};
+            CU(cudaSetDevice(c->cfg.device));
+            CU(cudaStreamSynchronize(c->stream));
+            CU(cudaMemcpyFromSymbol(h, g_tisph_check, sizeof(h)));
+#ifdef TISPH_CHECKS
+            *value = h[0] ? h[0] + h[1] * 1e-6 : 0.0;     // count + first failing line / 1e6
+#else
+            *value = -1.0;                                // checks are compiled out
+#endif
+            return TISPH_OK;
+        }
         case TISPH_P_DENSITY_MODE: *value = c->cfg.density_mode; return TISPH_OK;
         case TISPH_P_VOLUME_MODE: *value = c->cfg.volume_mode; return TISPH_OK;
         case TISPH_P_DIAGNOSTICS: *value = c->diagnostics; return TISPH_OK;

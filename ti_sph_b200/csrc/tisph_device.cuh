@@ -7,6 +7,20 @@
 
 namespace tisph {
 
+// Debug build (-DTISPH_CHECKS, `TISPH_CHECKS=1 python -m ti_sph_b200.build --force`): index bounds
+// of the shared-memory tiles, pending lists and list-pool rows are checked on the device and
+// counted; tisph_get_param(TISPH_P_STAT_CHECK_FAILURES) reads {count, first failing line}.
+// compute-sanitizer is not available on the B200 pool, so this is the memory checker of the repo.
+__device__ int g_tisph_check[2];
+#ifdef TISPH_CHECKS
+#define TISPH_CHECK(cond)                                                             \
+    do {                                                                              \
+        if (!(cond)) { if (atomicAdd(&g_tisph_check[0], 1) == 0) g_tisph_check[1] = __LINE__; } \
+    } while (0)
+#else
+#define TISPH_CHECK(cond) do { } while (0)
+#endif
+
 constexpr int MAT_BOUNDARY = 0;   // partice_systemv4.py:24
 constexpr int MAT_FLUID = 1;      // partice_systemv4.py:25
 

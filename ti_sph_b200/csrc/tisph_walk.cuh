@@ -298,6 +298,7 @@ __device__ __forceinline__ void filter8(uint32_t a0, uint32_t e0, float2 xi2, fl
         }
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
+            TISPH_CHECK(pend + 2 <= LCAP);
             float2 dx = __fadd2_rn(xi2, make_float2(c[k].x, c[k].y));
             float2 dy = __fadd2_rn(yi2, make_float2(c[k].z, c[k].w));
             float2 dz = __fadd2_rn(zi2, cz[k]);
@@ -395,6 +396,7 @@ k_density_list(SimParams sp, const int* __restrict__ cell_end, const int2* __res
                     if (AKINCI) mb = __float_as_int(Q[g].z);
                 }
                 const int slot = pair_slot(p, G.nsplit);
+                TISPH_CHECK(slot >= 0 && slot < TCAP / 2);
                 T[2 * slot] = make_float4(-a.x, -b.x, -a.y, -b.y);
                 T[2 * slot + 1] = make_float4(-a.z, -b.z, __int_as_float(ma), __int_as_float(mb));
             }
@@ -426,6 +428,7 @@ k_density_list(SimParams sp, const int* __restrict__ cell_end, const int2* __res
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
                             const uint32_t e = lds_u16(sL + (k4 + j) * (2 * NB_THREADS));
+                            TISPH_CHECK(e <= (uint32_t)E_DUMMY && k4 + j < LCAP);
                             const uint32_t a = sT + ((e & ~1u) << 4) + ((e & 1u) << 2);   // pair slot * 32 + lane * 4
                             const float dx = pi.x + lds_f32(a), dy = pi.y + lds_f32(a + 8), dz = pi.z + lds_f32(a + 16);
                             const float d2 = dist2_exact(dx, dy, dz);
@@ -437,8 +440,11 @@ k_density_list(SimParams sp, const int* __restrict__ cell_end, const int2* __res
                             if (AKINCI) wbsum += __float_as_int(lds_f32(a + 24)) == MAT_BOUNDARY ? w : 0.f;
                             ew[j] = tbase | e;
                         }
-                        if ((k4 >> 2) < groom)
+                        if ((k4 >> 2) < groom) {
+                            TISPH_CHECK(s_row >= 0 && s_row + 1 + gword + (k4 >> 2) < pool_rows_cap &&
+                                        gword + (k4 >> 2) < need);
                             *gp = make_uint2(ew[0] | (ew[1] << 16), ew[2] | (ew[3] << 16));
+                        }
                     }
                     gword += nd >> 2;
                     // move the remainder (< 4 entries) to the front
@@ -503,6 +509,7 @@ __device__ __forceinline__ void stage_force_tile(const CellRanges& R, int tile0,
             pr = d.y;
         }
         const int slot = nsplit > 0 ? cand_slot(e, nsplit) : e;
+        TISPH_CHECK(slot >= 0 && slot < TCAP);
         tP[slot] = p; tV[slot] = v; tR[slot] = pr;
     }
 }
@@ -589,8 +596,10 @@ k_force_list(SimParams sp, const int* __restrict__ cell_end, const int2* __restr
         const float rho_i = di.x, pr_i = di.y;
         const float nub_i = sp.visc_bound_c / (2.0f * rho_i);     // wcsphv2.py:76
         ForceAcc A = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        TISPH_CHECK(item_row[it] >= 0);
         const uint2* gl = Lg + (size_t)item_row[it] * NB_THREADS + tid;
         const int nw = walker ? (int)gl[0].x : 0;                 // words of 4 entries (count row)
+        TISPH_CHECK(nw >= 0 && nw <= KCAP / 4);
         gl += NB_THREADS;
         uint2 w = nw > 0 ? gl[0] : make_uint2(0u, 0u);
         if (G.total <= TCAP) {
@@ -604,6 +613,7 @@ k_force_list(SimParams sp, const int* __restrict__ cell_end, const int2* __restr
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     const uint32_t e = e4[j];                              // slot of tile 0 (or its dummy)
+                    TISPH_CHECK(e <= (uint32_t)E_DUMMY);
                     const uint32_t a = sP + 16u * e;
                     const float4 pj = lds_f32x4(a);
                     const float4 vj = lds_f32x4(a + V_OFF);
