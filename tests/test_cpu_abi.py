@@ -82,3 +82,21 @@ def test_lines_helper():
     pts, idx = getlines(sc.DEMO_3D["configuration"])
     pts = np.asarray(pts.to_numpy() if hasattr(pts, "to_numpy") else pts)
     assert pts.shape == (8, 3) and len(np.asarray(idx.to_numpy() if hasattr(idx, "to_numpy") else idx)) == 24
+
+
+def test_enum_values_of_the_header_match_the_ctypes_binding():
+    """tisph_field / tisph_stage / tisph_param / tisph_status: the numbers in include/tisph.h are the
+    numbers ti_sph_b200/_capi.py uses"""
+    text = open(os.path.join(ROOT, "include", "tisph.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    values = {m.group(1): int(m.group(2)) for m in re.finditer(r"\b(TISPH_[A-Z0-9_]+)\s*=\s*(-?\d+)", text)}
+    assert len(values) >= 40
+    for name, value in values.items():
+        for prefix, strip in (("TISPH_F_", "F_"), ("TISPH_STAGE_", "STAGE_"), ("TISPH_P_", "P_")):
+            if name.startswith(prefix):
+                assert getattr(_capi, strip + name[len(prefix):]) == value, name
+    assert values["TISPH_ERR_NO_DEVICE"] == _capi.ERR_NO_DEVICE
+    fields = sorted(v for k, v in values.items() if k.startswith("TISPH_F_"))
+    assert fields == list(range(len(fields)))                       # dense numbering, no duplicates
+    params = sorted(v for k, v in values.items() if k.startswith("TISPH_P_"))
+    assert params == list(range(len(params)))
