@@ -59,13 +59,15 @@ class FieldView:
         return torch.as_tensor(self, device=device or "cuda")
 
     def to_taichi(self):
+        """mirror into a Taichi field (kept and refilled on later calls, so that a GUI loop such as
+        main_3d.py:41 `scene.particles(ps.x, ...)` does not allocate a field per frame)"""
         import taichi as ti     # optional: only for the ggui hand-off
         a = self.to_numpy()
-        if a.ndim == 2:
-            f = ti.Vector.field(a.shape[1], dtype=ti.f32 if a.dtype == np.float32 else ti.i32,
-                                shape=a.shape[0])
-        else:
-            f = ti.field(dtype=ti.f32 if a.dtype == np.float32 else ti.i32, shape=a.shape[0])
+        f = getattr(self, "_ti_field", None)
+        if f is None or tuple(f.shape) != a.shape[:1]:
+            dt = ti.f32 if a.dtype == np.float32 else ti.i32
+            f = ti.Vector.field(a.shape[1], dtype=dt, shape=a.shape[0]) if a.ndim == 2 else ti.field(dtype=dt, shape=a.shape[0])
+            self._ti_field = f
         f.from_numpy(a)
         return f
 
