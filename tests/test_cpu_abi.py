@@ -100,3 +100,21 @@ def test_enum_values_of_the_header_match_the_ctypes_binding():
     assert fields == list(range(len(fields)))                       # dense numbering, no duplicates
     params = sorted(v for k, v in values.items() if k.startswith("TISPH_P_"))
     assert params == list(range(len(params)))
+
+
+def test_lines_helper_returns_taichi_fields_when_taichi_is_importable():
+    """main_3d.py:21,43 hands the result to ggui scene.lines; with a `taichi` module on the path
+    (here: the stand-in of tests/golden/ti_emu) the helper must return fields, not arrays"""
+    import subprocess
+    import sys
+    code = ("import sys; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+            "from utils.lines import getlines\n"
+            "from ti_sph_b200 import scene as sc\n"
+            "p, i = getlines(sc.DEMO_3D['configuration'])\n"
+            "import taichi\n"
+            "assert isinstance(p, taichi.Field) and isinstance(i, taichi.Field)\n"
+            "assert p.to_numpy().shape == (8, 3) and i.to_numpy().shape == (24,)\n"
+            "assert p.to_numpy().max() == 5.0 and sorted(set(i.to_numpy())) == list(range(8))\n"
+            "print('ok')\n") % (ROOT, os.path.join(ROOT, "tests", "golden", "ti_emu"))
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-1500:]
