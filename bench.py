@@ -31,12 +31,17 @@ BYTES_FORCE = 68.0      # fused forces+advect+walls: R {x,v,mass,volume,material
 BYTES_DENSITY = {"reference": 8.0, "summed": 24.0}     # R x 12 + mass 4, W rho 4 + p 4 (rho = mass W(0) needs no x)
 
 
-def measured_traffic(workload, kernel):
-    """dram__bytes_read+write per launch of `kernel` from the committed ncu --set full capture
-    (profiles/r01_traffic.json, written by scripts/ncu_summary.py), or None."""
+COUNTERS = "profiles/r02_counters.json"
+SM_COUNT, SMSP_PER_SM = 148, 4
+
+
+def ncu_counters(workload, mode, kernel):
+    """Per-PARTICLE counters of `kernel` from the committed `ncu --set full` capture of this workload
+    (profiles/r02_counters.json, written by scripts/ncu_summary.py): DRAM bytes (read + write), warp
+    instructions, FMA-pipe busy cycles.  None when the workload / mode was not captured."""
     try:
-        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
-            return json.load(f).get(workload, {}).get(kernel)
+        with open(os.path.join(ROOT, COUNTERS)) as f:
+            return json.load(f).get(f"{workload}/{mode}", {}).get(kernel)
     except Exception:
         return None
 
@@ -115,25 +120,19 @@ class ClockSampler:
 
 
 def workload_scene(name, with_mesh=True):
-    """BASELINE.md configurations.  C4 adds a mesh-sampled boundary: data/models/Dragon_50k.obj when
-    the user has put it there (it is the reference's asset and is not copied into this repo),
-    otherwise a procedural 50,000-triangle torus of similar size."""
+    """BASELINE.md configurations.  C4 adds the mesh-sampled boundary of the reference's own asset,
+    data/models/Dragon_50k.obj (an input fixture of this repo), voxelised at pitch 2r = 0.01 and set
+    down on the floor inside the padded domain."""
     from ti_sph_b200 import scene as sc
     s = sc.bench_scene(name)
     if name == "C4" and with_mesh:
         from ti_sph_b200 import mesh
         path = os.path.join(ROOT, "data", "models", "Dragon_50k.obj")
-        body = {"scale": [1, 1, 1], "rotationAngle": 0, "rotationAxis": [0, 1, 0], "color": [255, 255, 255],
-                "velocity": [0.0, 0.0, 0.0], "density": 1000.0}
-        if os.path.exists(path):
-            v, _ = mesh.load_obj(path)
-            body.update(geometryFile=path, translation=list(np.array([1.0, 0.06, 0.75]) - [v[:, 0].mean(), v[:, 1].min(), v[:, 2].mean()]))
-        else:
-            path = os.path.join(tempfile.gettempdir(), "tisph_c4_torus_50k.obj")
-            if not os.path.exists(path):
-                mesh.write_obj(path, *mesh.torus(0.45, 0.12, (0.0, 0.0, 0.0), nu=250, nv=100))
-            body.update(geometryFile=path, translation=[1.0, 0.25, 0.75])
-        s["rigidBodies"] = [body]
+        v, _ = mesh.load_obj(path)
+        s["rigidBodies"] = [{
+            "geometryFile": path, "scale": [1, 1, 1], "rotationAngle": 0, "rotationAxis": [0, 1, 0],
+            "color": [255, 255, 255], "velocity": [0.0, 0.0, 0.0], "density": 1000.0,
+            "translation": [float(t) for t in np.array([1.0, 0.06, 0.75]) - [v[:, 0].mean(), v[:, 1].min(), v[:, 2].mean()]]}]
     return s
 
 
@@ -158,7 +157,9 @@ def cpu_leg(workload, mode, steps, warmup, target_particles):
     """Times the CPU oracle (restatement of the reference's kernels, oracle/) on host cores."""
     from oracle.oracle import Gen2Oracle, lib
     scene = sample_scene(workload, target_particles)
-    ora = Gen2Oracle(scene, density_mode=mode)
+    # torchrun exports OMP_NUM_THREADS=1: take every core this process may run on, explicitly
+    threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    ora = Gen2Oracle(scene, density_mode=mode, threads=threads)
     cores = lib().ora_num_threads()
     for _ in range(warmup):
         ora.step_fast(1)
@@ -178,8 +179,13 @@ def run_reference_impl(args):
     if rank != 0:
         return
     leg = cpu_leg(args.workload, args.mode, args.steps, args.warmup, args.ref_particles)
+    try:                                        # re-probe in every run
+        import taichi  # noqa: F401
+        taichi_state = "importable, but the reference checkout does not travel to this box: CPU restatement timed"
+    except Exception as e:
+        taichi_state = f"not importable ({type(e).__name__})"
     line = {
-        "impl": "reference", "metric": METRIC, "value": leg["value"], "unit": UNIT,
+        "impl": "reference", "taichi": taichi_state, "metric": METRIC, "value": leg["value"], "unit": UNIT,
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": leg["ms_per_step"], "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -194,19 +200,19 @@ def run_reference_impl(args):
 
 
 # ----------------------------------------------------------------------------- GPU arm
-def also_measure(workload, args, torch, stream):
-    """device-resident timing of a second workload with the rules of the main one (single GPU)"""
+def also_measure(workload, mode, pre, chain, args, torch, stream):
+    """device-resident timing of a second workload / density mode with the rules of the main one (single GPU)"""
     from core.partice_system.partice_systemv4 import ParticleSystemV4
-    ps = ParticleSystemV4(workload_scene(workload), density_mode=args.mode)
+    ps = ParticleSystemV4(workload_scene(workload), density_mode=mode)
     eng = ps.engine
     eng.set_stream(stream.cuda_stream)
-    eng.step(args.pre_steps)
+    eng.step(pre)
     eng.save_state()
 
     def run(k):
         done = 0
         while done < k:
-            m = min(args.chain, k - done)
+            m = min(chain, k - done)
             eng.restore_state()
             eng.step(m)
             done += m
@@ -221,10 +227,50 @@ def also_measure(workload, args, torch, stream):
     ms = ev0.elapsed_time(ev1) / args.steps
     st = eng.stage_times(False)
     n = eng.particle_num
+    pairs = int(eng.download(_K().F_NEIGHBOR_COUNT).astype(np.int64).sum())
+    fb = int(eng.get_param(_K().P_STAT_FALLBACK_FORCE))
     eng.close()
-    return {"workload": f"{workload}: {n} particles", "value": n / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms,
-            "stage_ms": {k: st[k] for k in ("update_ms", "density_ms", "force_ms")},
+    return {"workload": f"{workload}: {n} particles", "density_mode": mode, "value": n / (ms * 1e-3), "unit": UNIT,
+            "ms_per_step": ms, "stage_ms": {k: st[k] for k in ("update_ms", "density_ms", "force_ms")},
+            "step_hbm_frac": BYTES_STEP[mode] * n / (ms * 1e-3) / 1e9 / measured_peaks()[0],
+            "pair_interactions_per_s": 2.0 * pairs / (ms * 1e-3), "fallback_force_items": fb,
+            "state": f"after {pre} steps from the t=0 lattice, replayed in chains of {chain}",
             "l2": "state fits L2 (small workload)" if n * 96 <= 126e6 else "state larger than L2"}
+
+
+def _K():
+    from ti_sph_b200 import _capi
+    return _capi
+
+
+def sharded_check(args, rank, world, local_rank, comm):
+    """Correctness of the multi-process path, outside the timed region: two sharded steps of a
+    <= 1 M-particle cut of the workload against the single engine on rank 0 -- the same particle ids
+    after migration, x and v within 1e-5 (relative to the block size / the initial speed)."""
+    from ti_sph_b200.sharded import ShardedSim
+    scene = sample_scene(args.workload, 1_000_000)
+    small = ShardedSim(scene, rank, world, comm=comm, density_mode=args.mode, device=local_rank)
+    small.step(2)
+    got = small.dump()                       # gathered on every rank, rank order = global cell order
+    small.engine.sync()
+    small.close()
+    if rank != 0:
+        return None
+    from core.partice_system.partice_systemv4 import ParticleSystemV4
+    ps = ParticleSystemV4(scene, device=local_rank, density_mode=args.mode)
+    ps.engine.step(2)
+    want = ps.dump()
+    ids = ps.engine.download(_K().F_ORIG_ID)
+    ps.engine.close()
+    n = len(ids)
+    if len(got["orig_id"]) != n or not np.array_equal(np.sort(got["orig_id"]), np.arange(n, dtype=np.int32)):
+        return f"FAILED: {len(got['orig_id'])} particles / ids are not a permutation of 0..{n - 1}"
+    a, b = np.argsort(got["orig_id"], kind="stable"), np.argsort(ids, kind="stable")
+    dx = float(np.abs(got["position"][a].astype(np.float64) - want["position"][b]).max())
+    dv = float(np.abs(got["velocity"][a].astype(np.float64) - want["velocity"][b]).max())
+    vscale = float(np.abs(want["velocity"]).max())
+    ok = dx <= 1e-5 * 1.0 and dv <= 1e-5 * max(vscale, 1.0)
+    return ("ok" if ok else "FAILED") + f": {n} particles x{world} ranks, 2 steps, max |dx| {dx:.2e} m, max |dv| {dv:.2e} m/s"
 
 
 def run_gpu(args):
@@ -400,8 +446,18 @@ def run_gpu(args):
         k = max(sim.profile.get("steps", 1), 1)
         log(f"[bench] rank {rank} host phases per step (ms): " +
             ", ".join(f"{n} {1e3 * v / k:.3f}" for n, v in sim.profile.items() if n != "steps"))
-    if rank != 0:
-        return
+    check = None
+    if sim is not None:
+        import torch.distributed as dist
+        if not args.no_check:
+            check = sharded_check(args, rank, world, local_rank, sim.comm)
+            if rank == 0:
+                log(f"[bench] sharded_check: {check}")
+        if rank != 0:
+            sim.close()
+            dist.barrier()
+            dist.destroy_process_group()
+            return
     # ---- roofline of the dominant kernel, measured live with CUDA events on the engine's stream ----
     n_local = eng.particle_num
     cand = {"density": ("k_density_list (+k_density_fb): boundary volume, density summation, clamp, Tait EOS",
@@ -411,21 +467,42 @@ def run_gpu(args):
     dom = max(cand, key=lambda k: cand[k][2])
     kname, kbytes, kms, ktag = cand[dom]
     achieved = kbytes * n_local / (kms * 1e-3) / 1e9 if kms > 0 else 0.0
-    traffic = measured_traffic(args.workload, ktag)
+    # The bound that binds is instruction issue / the FP32 pipe, not HBM: the committed ncu
+    # capture gives warp instructions and FMA-pipe cycles per particle, the live kernel time turns them
+    # into fractions of the issue and pipe peaks (SMs x 4 schedulers x SM clock).
+    sm_hz = 1e6 * float((clk or {}).get("sm_mhz") or 1965.0)
+    slots_per_s = SM_COUNT * SMSP_PER_SM * sm_hz
+    per_kernel = {}
+    for key, (_, _, kms_k, tag) in cand.items():
+        c = ncu_counters(args.workload, args.mode, tag)
+        if c and kms_k > 0:
+            per_kernel[key] = {
+                "issue_frac": c["warp_inst_per_particle"] * n_local / (kms_k * 1e-3) / slots_per_s,
+                "fp32_pipe_frac": c["fma_pipe_cycles_per_particle"] * n_local / (kms_k * 1e-3) / slots_per_s,
+                "traffic": c["dram_bytes_per_particle"] * n_local}
+    cdom = per_kernel.get(dom, {})
+    pairs = int(eng.download(K.F_NEIGHBOR_COUNT).astype(np.int64).sum())       # of the last step, this rank
     roofline = {
         "bound": "hbm", "kernel": kname, "achieved": achieved,
         "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "peak_kind": peak_kind,
-        "traffic": traffic, "bytes_per_particle": kbytes, "launch_ms": kms,
+        "traffic": cdom.get("traffic"), "bytes_per_particle": kbytes, "launch_ms": kms,
+        "issue_frac": cdom.get("issue_frac"), "fp32_pipe_frac": cdom.get("fp32_pipe_frac"),
+        "pairs_per_s": 2.0 * pairs / (ms * 1e-3),
+        "per_kernel": per_kernel,
         "step_hbm_frac": BYTES_STEP[args.mode] * n_total / (ms * 1e-3) / 1e9 / hbm_peak / world,
         "stage_ms": {k: stage[k] for k in ("update_ms", "density_ms", "force_ms")},
         "stage_hbm_frac": {"update": (16 + 2 + 76) * n_local / max(stage["update_ms"], 1e-9) / 1e6 / hbm_peak,
                            "density": BYTES_DENSITY[args.mode] * n_local / max(stage["density_ms"], 1e-9) / 1e6 / hbm_peak,
                            "force": BYTES_FORCE * n_local / max(stage["force_ms"], 1e-9) / 1e6 / hbm_peak},
         "work_items_last_step": items,
-        "traffic_note": "dram read+write bytes per launch, ncu --set full capture of this workload (profiles/r01_traffic.json)",
-        "note": "both walks are bound by FP32 instruction issue and shared-memory gathers, not HBM: at the "
-                "reference's h = 4 x spacing every particle filters 1728 candidates and evaluates ~243 pairs per "
-                "walk (ncu: issue-active 72-77 %, shared wavefronts 70-75 %); see DESIGN.md section 5",
+        "definitions": "traffic = DRAM read+write bytes per launch on this rank: per-particle bytes of the committed "
+                       f"ncu --set full capture ({COUNTERS}) x this rank's particles; issue_frac = warp instructions / "
+                       "(kernel time x 148 SMs x 4 schedulers x SM clock); fp32_pipe_frac = FMA-pipe busy cycles over "
+                       "the same denominator (a packed f32x2 instruction holds the pipe two cycles); pairs_per_s = "
+                       "neighbour pairs evaluated per second by this rank (sum of the neighbour counts, two walks per step)",
+        "note": "both walks are bound by instruction issue / the FP32 pipe and by shared-memory gathers, not by HBM: "
+                "at the reference's h = 4 x spacing every particle tests ~1730-2030 candidates and evaluates ~250 "
+                "pairs in each walk; see DESIGN.md section 5 and profiles/",
     }
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
@@ -451,13 +528,28 @@ def run_gpu(args):
     line["e2e"] = e2e
     if cpu is not None:
         line["cpu_baseline"] = cpu
+    if check is not None:
+        line["sharded_check"] = check
     if world == 1 and args.workload == "C5" and not args.no_also:
-        # the metric is quoted at 1 M and at 16 M particles: the 1 M run (C3) rides along
-        try:
-            line["also_measured"] = {"C3": also_measure("C3", args, torch, stream)}
-        except Exception as e:                      # never lose the main line over the side measurement
-            line["also_measured"] = {"C3": {"error": str(e)[:200]}}
+        # the metric is quoted at 1 M and at 16 M particles, and `summed` is the mode in which the Tait
+        # pressure works: both ride along in config.also (1 M: the state after 50 steps, BASELINE.md;
+        # summed C5: steps 2..5 -- with a working pressure the reference's fixed dt = 2e-4 is beyond the CFL
+        # limit at r = 0.005 and the block disintegrates within ~10 steps)
+        eng.close()
+        also = {}
+        for key, (wl, mode, pre, chain) in {"C3_1M": ("C3", args.mode, 50, 5),
+                                            "C5_16M_summed": ("C5", "summed", 2, 3)}.items():
+            try:
+                also[key] = also_measure(wl, mode, pre, chain, args, torch, stream)
+            except Exception as e:                  # never lose the main line over a side measurement
+                also[key] = {"error": str(e)[:200]}
+        line["config"]["also"] = also
     print(json.dumps(line), flush=True)
+    if sim is not None:
+        import torch.distributed as dist
+        sim.close()
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 def main():
@@ -475,7 +567,8 @@ def main():
     ap.add_argument("--cpu-particles", type=int, default=1000000, help="size of the cpu_baseline sample")
     ap.add_argument("--ref-particles", type=int, default=1000000, help="sample size of --impl reference")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-also", action="store_true", help="skip the 1 M-particle side measurement of the C5 run")
+    ap.add_argument("--no-also", action="store_true", help="skip the side measurements of the C5 run (1 M particles; summed mode)")
+    ap.add_argument("--no-check", action="store_true", help="skip the sharded-vs-single-engine check of a multi-GPU run")
     args = ap.parse_args()
     if args.warmup < 3:
         log("[bench] warm-up raised to 3 (timing rules)")

@@ -222,6 +222,15 @@ class Gen2Oracle:
                              _p(self.density), _p(self.pressure), _p(self.material),
                              _p(self.scan), _p(self.dvel), _p(self.a_pressure))
 
+    def force_magnitudes(self, density_pre):
+        """(sum |non-pressure term|, sum |pressure term|) per particle: the scale of the rounding error of
+        the two acceleration sums (test support; call after compute_pressure_force, before advert)."""
+        mnp, mp = np.zeros(self.n, np.float32), np.zeros(self.n, np.float32)
+        lib().ora_force_magnitudes(C.byref(self.cfg), self.n, _p(self.x), _p(self.v), _p(self.mass),
+                                   _p(self.volume), _p(_f32(density_pre)), _p(self.density), _p(self.pressure),
+                                   _p(self.material), _p(self.scan), _p(mnp), _p(mp))
+        return mnp, mp
+
     def advert(self):
         lib().ora_advect(C.byref(self.cfg), self.n, _p(self.x), _p(self.v), _p(self.dvel),
                          _p(self.material))
@@ -250,6 +259,7 @@ class Gen2Oracle:
         if trace:
             t.update(density=self.density.copy(), pressure=self.pressure.copy(),
                      a_pressure=self.a_pressure.copy(), d_velocity=self.dvel.copy())
+            t["mag_nonpressure"], t["mag_pressure"] = self.force_magnitudes(t["density_pre"])
         self.advert()
         if trace:
             t.update(x_advected=self.x.copy(), v_advected=self.v.copy())

@@ -319,6 +319,46 @@ void ora_non_pressure(const ora_config *c, int n, const float *x, const float *v
     }
 }
 
+/* Test support (not a reference kernel): per fluid particle the sum of the MAGNITUDES of the terms that
+ * ora_non_pressure (|g| + every pair's cohesion and viscosity vector) and ora_pressure_force (every
+ * pair's pressure vector) add up, in double.  An f32 sum of N terms carries a rounding error bounded
+ * by a multiple of eps * sum |term|, so this -- not |a| itself, which is what is left after the terms
+ * cancel -- is the scale a relative tolerance on the accelerations refers to.
+ * `density` / `pressure` are the post-EOS values (after ora_eos). */
+void ora_force_magnitudes(const ora_config *c, int n, const float *x, const float *v, const float *mass,
+                          const float *volume, const float *density_pre, const float *density,
+                          const float *pressure, const int32_t *material, const int32_t *scan,
+                          float *mag_np, float *mag_p) {
+#pragma omp parallel for schedule(dynamic, 256)
+    for (int i = 0; i < n; ++i) {
+        mag_np[i] = 0.0f;
+        mag_p[i] = 0.0f;
+        if (material[i] != MAT_FLUID) continue;
+        double snp = sqrt((double)c->g[0] * c->g[0] + (double)c->g[1] * c->g[1] + (double)c->g[2] * c->g[2]);
+        double sp = 0.0;
+        FOR_ALL_NEIGHBORS3(c, scan, x, i, j, {
+            float vij[3] = {v[3 * (size_t)i] - v[3 * (size_t)j],
+                            v[3 * (size_t)i + 1] - v[3 * (size_t)j + 1],
+                            v[3 * (size_t)i + 2] - v[3 * (size_t)j + 2]};
+            float gw[3];
+            cubic_kernel_derivative(c, r_, gw);
+            double gn = sqrt((double)gw[0] * gw[0] + (double)gw[1] * gw[1] + (double)gw[2] * gw[2]);
+            double mn = fmin(0.0, (double)vdot(vij, r_, 3)) / ((double)vdot(r_, r_, 3) + c->eps_h2);
+            if (material[j] == MAT_FLUID) {
+                snp += fabs(0.01 / mass[i] * mass[j]) * rn_ * cubic_kernel(c, rn_);
+                snp += fabs(mass[j] * (c->visc_fluid_c / ((double)density_pre[i] + density_pre[j])) * mn) * gn;
+                sp += fabs(mass[j] * ((double)pressure[i] / ((double)density[i] * density[i]) +
+                                      (double)pressure[j] / ((double)density[j] * density[j]))) * gn;
+            } else {
+                snp += fabs(c->ps_density0 * volume[j] * (c->visc_bound_c / (2.0 * density_pre[i])) * mn) * gn;
+                sp += fabs(c->rho0 * volume[j] * ((double)pressure[i] / ((double)density[i] * density[i]))) * gn;
+            }
+        });
+        mag_np[i] = (float)snp;
+        mag_p[i] = (float)sp;
+    }
+}
+
 /* wcsphv2.py:45-48 (launch A): clamp + Tait EOS for every particle */
 void ora_eos(const ora_config *c, int n, float *density, float *pressure) {
 #pragma omp parallel for schedule(static)

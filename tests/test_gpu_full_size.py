@@ -135,9 +135,8 @@ def test_c2_shipped_demo_3d_scene_against_the_oracle_and_survey_values():
 
 
 def test_c4_four_million_particles_with_a_mesh_sampled_boundary():
-    """BASELINE config C4: 200 x 200 x 100 fluid block (r = 0.005) over a voxelised 50,000-triangle
-    mesh (the reference's Dragon_50k.obj if it has been put under data/models, else a procedural
-    torus), one step against the oracle fed with the same boundary points"""
+    """BASELINE config C4: 200 x 200 x 100 fluid block (r = 0.005) over the voxelised Dragon_50k.obj
+    (the reference's asset, data/models/), one step against the oracle fed with the same boundary points"""
     import sys
     import os
     sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -151,7 +150,8 @@ def test_c4_four_million_particles_with_a_mesh_sampled_boundary():
     eng = ps.engine
     pts = ps.rigidBodiesConfig[0]["voxelized_points"]
     n = ps.particle_num[None]
-    assert n == 4_000_000 + len(pts) and len(pts) > 50_000
+    assert scene["rigidBodies"][0]["geometryFile"].endswith("Dragon_50k.obj")
+    assert n == 4_000_000 + len(pts) and abs(len(pts) - 129_815) <= 40          # tests/golden/dragon_c4_voxels.npz
     bare = dict(scene, rigidBodies=[dict(scene["rigidBodies"][0])])
     ora = Gen2Oracle(bare, volume_mode="akinci", boundary_points=pts)
     assert ora.n == n

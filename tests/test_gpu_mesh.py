@@ -105,3 +105,52 @@ def test_rigid_body_scene_through_the_drop_in_class(tmp_path):
         assert rel_err(d["position"], ora.x, floor=0.04) < 5 * RTOL
         assert rel_err(ps.volume.to_numpy(), ora.volume) < RTOL
         ps.engine.close()
+
+
+def test_dragon_50k_voxelised_in_the_c4_placement_matches_the_float64_golden():
+    """The reference's only mesh asset (data/models/Dragon_50k.obj, partice_systemv4.py:259-277) at the
+    C4 placement and pitch: the GPU sampler against tests/golden/dragon_c4_voxels.npz (float64
+    separating-axis surface + scipy binary_fill_holes, written by tests/golden/make_dragon_golden.py).
+    The mesh is closed but not 2-manifold (74,968 edges with two faces, 16 with four, none with one),
+    so the outside flood fill of the sampler is well defined: fill = everything the flood cannot reach."""
+    import os
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    from bench import workload_scene
+    gold = np.load(os.path.join(root, "tests", "golden", "dragon_c4_voxels.npz"))
+    scene = workload_scene("C4")
+    body = scene["rigidBodies"][0]
+    assert body["geometryFile"].endswith(os.path.join("data", "models", "Dragon_50k.obj"))
+    assert np.allclose(body["translation"], gold["translation"])
+    v, f = mesh.load_obj(body["geometryFile"])
+    assert (len(v), len(f)) == (int(gold["n_vertices"]), int(gold["n_faces"])) == (25007, 50000)
+    edges = np.sort(np.concatenate([f[:, [0, 1]], f[:, [1, 2]], f[:, [2, 0]]]), axis=1)
+    _, cnt = np.unique(edges, axis=0, return_counts=True)
+    assert np.bincount(cnt).tolist() == gold["edge_face_histogram"].tolist() == [0, 0, 74968, 0, 16]   # closed surface
+    pitch = float(gold["pitch"])
+    dims, lo = tuple(int(d) for d in gold["dims"]), gold["lo"].astype(np.int64)
+    n = int(np.prod(dims))
+    want_surface = np.unpackbits(gold["surface"])[:n].reshape(dims).astype(bool)
+    want_full = np.unpackbits(gold["filled"])[:n].reshape(dims).astype(bool)
+    assert (int(want_surface.sum()), int(want_full.sum())) == (39759, 129815)
+    vt = mesh.transform_vertices(v, body)
+
+    def occupancy(points):
+        k = np.round(points.astype(np.float64) / pitch).astype(np.int64) - lo
+        assert np.all(k >= 0) and np.all(k < np.array(dims))
+        occ = np.zeros(dims, bool)
+        occ[k[:, 0], k[:, 1], k[:, 2]] = True
+        assert occ.sum() == len(points)                       # no duplicates
+        return occ
+
+    surf = occupancy(mesh.voxelize(vt, f, pitch, fill=False))
+    full = occupancy(mesh.sample_rigid_body(dict(body), pitch))
+    # f32 (GPU) vs f64 (golden) may disagree only where a triangle touches a voxel face within rounding
+    assert int((surf ^ want_surface).sum()) <= 40
+    diff = full ^ want_full
+    assert int(diff.sum()) <= 40 and not np.any(diff & ~(surf | want_surface))    # the interior is identical
+    pts = np.argwhere(full) + lo
+    assert np.array_equal(pts.min(0), lo + 1) and np.array_equal(pts.max(0), lo + np.array(dims) - 2)   # bbox
+    interior = full.sum() - surf.sum()
+    assert 0.68 < interior / full.sum() < 0.71            # 129,815 points, 90,056 of them strictly inside

@@ -14,7 +14,7 @@ CSRC = os.path.join(_HERE, "csrc")
 LIBDIR = os.path.join(_HERE, "lib")
 LIB = os.path.join(LIBDIR, "libtisph.so")
 SOURCES = ["tisph.cu"]
-HEADERS = ["tisph_kernels.cuh", "tisph_device.cuh", "tisph_walk.cuh", "tisph_shard.cuh", "tisph_gen1.cuh", "tisph_voxel.cuh"]
+HEADERS = ["tisph_kernels.cuh", "tisph_device.cuh", "tisph_walk.cuh", "tisph_lists.cuh", "tisph_shard.cuh", "tisph_gen1.cuh", "tisph_voxel.cuh"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 if os.environ.get("TISPH_CHECKS") == "1":       # debug build with device-side bounds checks (tisph_device.cuh)

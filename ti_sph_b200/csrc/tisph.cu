@@ -12,6 +12,7 @@
 #include "tisph.h"
 #include "tisph_kernels.cuh"
 #include "tisph_walk.cuh"
+#include "tisph_lists.cuh"
 #include "tisph_shard.cuh"
 #include "tisph_gen1.cuh"
 #include "tisph_voxel.cuh"
@@ -64,13 +65,14 @@ struct tisph_ctx {
     int* err_dev = nullptr;
     // work items of the neighbour walks + neighbour lists handed from walk 1 to walk 2
     int2* items = nullptr;
-    int items_cap = 0, list_items_cap = 0;
+    int items_cap = 0;
     int pool_rows_cap = 0;
+    int occ_dl = 0, occ_fl = 0;        // resident CTAs per SM of the two list kernels
     int* item_row = nullptr;
     StepCounters* ctr = nullptr;
     int *fb_d = nullptr, *fb_f = nullptr;
     unsigned char* item_flags = nullptr;
-    uint2* Lg = nullptr;
+    uint32_t* Lg = nullptr;
     int grid_dl = 0, grid_fl = 0, grid_dfb = 0, grid_ffb = 0;   // persistent grids (SMs x resident CTAs)
     void* staging = nullptr;
     size_t staging_bytes = 0;
@@ -138,6 +140,7 @@ static void fill_params(tisph_ctx* c) {
     s.density_mode = g.density_mode; s.volume_mode = g.volume_mode;
     float e = g.exponent;
     s.int_exponent = (e >= 1.0f && e <= 64.0f && e == floorf(e)) ? (int)e : 0;
+    s.one = 1.0f;
     s.own_key_lo = 0; s.own_key_hi = 0x7fffffff;
     s.walk_key_lo = 0; s.walk_key_hi = 0x7fffffff;
     s.ghost_walk = 1;
@@ -264,7 +267,7 @@ static int run_density(tisph_ctx* c) {
     // ghost cells: their density is needed by the force walk, but in the reference modes it is mass * W(0)
     c->sp.ghost_walk = (c->sp.density_mode == 0 && c->sp.volume_mode == 0) ? 0 : 1;
     auto kd = c->sp.volume_mode == 1 ? k_density_list<true> : k_density_list<false>;
-    kd<<<c->grid_dl, NB_THREADS, DL_SMEM, st>>>(
+    kd<<<c->grid_dl, NB_THREADS, c->sp.volume_mode == 1 ? DL_SMEM_AKINCI : DL_SMEM, st>>>(
         c->sp, c->cell_end, c->items, c->ctr, c->pool_rows_cap, c->variant == 1, c->P[b], c->V[b], c->Q[b],
         c->D, c->S, c->ncount, c->Lg, c->item_row, c->item_flags, c->fb_d, c->fb_f);
     k_density_fb<<<c->grid_dfb, NB_THREADS, DF_SMEM, st>>>(c->sp, c->cell_end, c->items, c->ctr, c->fb_d,
@@ -353,10 +356,8 @@ int tisph_create(const tisph_config* cfg, tisph_ctx** out) {
     A(dalloc(&c->err_dev, 4));
     {
         int64_t occupied_max = ncell < (int64_t)cap ? ncell : (int64_t)cap;
-        c->items_cap = (int)(occupied_max + (int64_t)cap / 32 + 2);
-        int64_t budget = (int64_t)cap / 28 + 1024;           // items that get a neighbour list (48 KiB each)
-        c->list_items_cap = (int)(budget < c->items_cap ? budget : c->items_cap);
-        if (cfg->generation == 1) { c->items_cap = 1; c->list_items_cap = 1; }   // gen-1 walks an explicit table
+        c->items_cap = (int)(occupied_max + (int64_t)cap / 64 + 2);
+        if (cfg->generation == 1) c->items_cap = 1;           // gen-1 walks an explicit table
     }
     if (cfg->generation == 1) {
         A(dalloc(&c->nbr, cap * G1_MAX_NEIGHBORS));
@@ -366,9 +367,15 @@ int tisph_create(const tisph_config* cfg, tisph_ctx** out) {
     A(dalloc(&c->ctr, 1));
     A(dalloc(&c->fb_d, (size_t)c->items_cap)); A(dalloc(&c->fb_f, (size_t)c->items_cap));
     A(dalloc(&c->item_flags, (size_t)c->items_cap));
-    c->pool_rows_cap = c->list_items_cap * POOL_ROWS_PER_FULL_ITEM;        // neighbour-list pool, ~1.75 KB per particle
-    A(dalloc(&c->Lg, (size_t)c->pool_rows_cap * NB_THREADS));
-    A(dalloc(&c->item_row, (size_t)c->items_cap));
+    // neighbour-list pool: rows of 32 words (128 B).  A warp of the density walk (4 targets) reserves 1 + the
+    // words of its longest lane: ~12 rows at the reference spacing, i.e. ~0.4 KB per particle; sized for
+    // 0.75 KB per particle plus slack.  Items that find the pool exhausted take the fallback force kernel.
+    {
+        int64_t rows = cfg->generation == 1 ? 1 : (int64_t)cap * 6 + 65536;
+        c->pool_rows_cap = (int)(rows < 0x7fffffff / 2 ? rows : 0x7fffffff / 2);
+    }
+    A(dalloc(&c->Lg, (size_t)c->pool_rows_cap * 32));
+    A(dalloc(&c->item_row, 16 * (size_t)c->items_cap));         // one row index per pass and warp
     c->staging_bytes = cap * 16 * 3;
     A(cudaMalloc(&c->staging, c->staging_bytes));
     if (e == cudaSuccess) {
@@ -382,7 +389,7 @@ int tisph_create(const tisph_config* cfg, tisph_ctx** out) {
         A(cudaMemsetAsync(c->cell_count, 0, (size_t)c->ncell * 4, c->stream));
         if (c->nbr_num) A(cudaMemsetAsync(c->nbr_num, 0, cap * 4, c->stream));
         A(cudaFuncSetAttribute(k_density_list<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DL_SMEM));
-        A(cudaFuncSetAttribute(k_density_list<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DL_SMEM));
+        A(cudaFuncSetAttribute(k_density_list<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DL_SMEM_AKINCI));
         A(cudaFuncSetAttribute(k_force_list<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FL_SMEM));
         A(cudaFuncSetAttribute(k_force_list<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FL_SMEM));
         A(cudaFuncSetAttribute(k_density_fb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DF_SMEM));
@@ -391,8 +398,10 @@ int tisph_create(const tisph_config* cfg, tisph_ctx** out) {
         A(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg->device));
         A(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_density_list<false>, NB_THREADS, DL_SMEM));
         c->grid_dl = sms * (occ > 0 ? occ : 1);
+        c->occ_dl = occ;
         A(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_force_list<true>, NB_THREADS, FL_SMEM));
         c->grid_fl = sms * (occ > 0 ? occ : 1);
+        c->occ_fl = occ;
         A(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_density_fb, NB_THREADS, DF_SMEM));
         c->grid_dfb = sms * (occ > 0 ? occ : 1);
         A(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_force_fb, NB_THREADS, FF_SMEM));

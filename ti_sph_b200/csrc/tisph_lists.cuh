@@ -1,0 +1,527 @@
+// tisph_lists.cuh -- the two neighbour walks of a WCSPH step on sm_100a, list path (the kernels
+// every benchmark runs; tisph_walk.cuh holds what they share with the fallback kernels).
+//
+// Measured on B200 (scripts/ubench_g8*.cu), and what this file is built on:
+//   * a packed f32x2 instruction (FADD2/FMUL2/FFMA2) occupies the FMA pipe for two cycles: packing
+//     saves issue slots, not arithmetic throughput;
+//   * LDS.128 with 32 distinct addresses costs 8 cycles per warp however the banks fall (12.8 for
+//     random 16-byte gathers); LDS.64 costs 2 when each half-warp hits 16 distinct 8-byte bank
+//     pairs, LDS.32 1.2-1.4 when conflict-free.  Gathers therefore use 8-byte records.
+//
+// Thread arrangement.  A work item is up to 64 target particles of one grid cell (k_items); the
+// CTA's 256 threads walk it in passes of 32 targets x 8 lanes.  Lane j of a target's group owns the
+// candidates whose tile slot s has s mod 8 == j; with m = s >> 3 (the slot's ROW, 0..253) a
+// candidate is named by one byte.  Rows alternate between two PARITY streams (m even / m odd),
+// and every lane consumes one entry of each stream per iteration, even groups in the order
+// (even, odd), odd groups (odd, even).  The 16 lanes of an LDS.64 phase (one even and one odd group)
+// then read 8-byte slots s = 8 m + j with s mod 16 = j (+8 for odd m): 16 distinct bank pairs,
+// no conflict, for any neighbour pattern.
+//
+// Tile.  The 27 neighbour cells of a cell are 9 contiguous ranges of the sorted arrays (z is the
+// fastest key digit); all of them are staged into shared memory once per item, candidate e in slot
+// cand_to_slot(e) (one tile of LT_CAP = 2032 candidates: 27 cells x 64 at the reference spacing is 1728, and the
+// lattice aliasing of a moving block reaches 2028; anything larger goes to the fallback kernels).
+//
+// Walk 1 (k_density_list): FILTER -- lane j tests its candidates two rows at a time (rows 2k and
+// 2k+1 are the two halves of a packed f32x2 value: FADD2/FMUL2/FFMA2, loads shared by the four
+// groups of a warp) against a cutoff widened by 1e-6 and pushes the survivors' row bytes to its two
+// pending streams in shared memory; DRAIN -- one (even, odd) pair of entries per iteration, packed:
+// exact IEEE test sqrt(d2) < h in the reference's evaluation order (bit-exact neighbour count) and
+// the kernel sum.  The drained byte pairs are copied to the warp's rows of the global neighbour-list
+// pool, four entries per 32-bit word, [word][lane]; an item in which one stream of one lane collects
+// more than 40 neighbours (crowded cells) is left to the fallback kernels.
+// Walk 2 (k_force_list): no filter -- every lane replays its byte list, gathers the neighbour's
+// {x,y} {z,psi} {vx,vy} {vz,rho} p/rho^2 from 8-byte planes and evaluates cohesion, artificial
+// viscosity and pressure for two neighbours at a time, branch-free; then advect + walls.
+#pragma once
+#include "tisph_walk.cuh"
+
+namespace tisph {
+
+constexpr int GL = 8;                            // lanes per target
+constexpr int PASS_T = NB_THREADS / GL;          // targets per pass (32)
+constexpr int LT_ROWS = 128;                     // tile rows of 16 candidates in the pair-packed filter arrays
+constexpr int LT_SLOTS = 2048;                   // 8-byte slots per plane (rows m = 0..255 of 8 slots)
+constexpr int LT_CAP = 2032;                     // candidates of one tile: rows m = 0..253
+constexpr int M_DUMMY = 254;                     // rows 254 (even stream) and 255 (odd stream) are always FAR
+constexpr int LCAP2 = 48;                        // pending entries per parity stream and lane (shared memory)
+constexpr int LSTRIDE = 2 * LCAP2 + 4;           // bytes of a lane's pending list (25 words: odd, so lanes spread over banks)
+constexpr int FCHUNK = 8;                        // row pairs filtered between drain checks
+// Neighbour-list pool (global memory): rows of 32 words (128 B).  A warp (4 targets x 8 lanes) takes one
+// count row plus as many list rows as its longest lane needs -- reserved after the walk, so nothing
+// is padded to a worst case: ~12 rows per warp (0.4 KB per particle) at the reference spacing.
+
+// Candidate -> slot.  While a block of particles is still lattice-like, the 16 candidates of an aligned
+// run are a (y, z) plane of a cell's 4 x 4 x 4 sub-lattice, and the plain map slot = candidate would hand
+// each lane (slot mod 8) and each parity stream (bit 3 of the slot) one z-column / half of the plane: the
+// lists of a target's eight lanes would differ by factors.  The map below permutes every aligned run
+// of 16 so that the 16 classes (slot mod 16) are diagonals of the sub-lattice, which a neighbourhood
+// ball cuts evenly:  with x = bits 4-5, y = bits 2-3, z = bits 0-1 of the candidate,
+//   slot = (e & ~15) | ((x - y) & 3) << 2 | ((x + y + z) & 3).
+__device__ __forceinline__ int cand_to_slot(int e) {
+    const int x = e >> 4, y = e >> 2, z = e;
+    return (e & ~15) | (((x - y) & 3) << 2) | ((x + y + z) & 3);
+}
+__device__ __forceinline__ int slot_to_cand(int s) {
+    const int x = s >> 4, chi = s >> 2, clo = s;
+    const int y = (x - chi) & 3;
+    return (s & ~15) | (y << 2) | ((clo - x - y) & 3);
+}
+
+__device__ __forceinline__ void sts_u8(uint32_t a, uint32_t v) {
+    asm volatile("st.shared.u8 [%0], %1;" :: "r"(a), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t lds_u8(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    return v;
+}
+
+// =======================================================================================
+// Walk 1: boundary volume, density summation, clamp, Tait EOS; builds the neighbour lists
+//   FXY[8k+j] = {-xa,-xb,-ya,-yb}, FZ[8k+j] = {-za,-zb}: a = slot 16k+j (row 2k), b = slot 16k+8+j (row 2k+1)
+//   GXY[s] = {x,y} of slot s (the drain's gathers; z comes from FZ)      GM[s] = material (Akinci volumes only)
+// A pass runs in two phases with different thread arrangements over the same (target, lane) lists:
+//   FILTER  thread = (lane j = warp index, target = lane id): the 32 threads of a warp test the SAME
+//           candidates against 32 targets, so the tile is read with broadcast loads;
+//   DRAIN   thread = (target = tid / 8, lane j = tid % 8): the arrangement of the file header, whose
+//           gathers are conflict-free.
+// The pending list of (target t, lane j) is LSTRIDE bytes at word LIST_J * j + LIST_T * t: consecutive t
+// (filter pushes) and the 4 x 8 (t, j) of a drain warp both fall into 32 different banks.
+// =======================================================================================
+constexpr int LIST_T = LSTRIDE / 4;              // 25 words
+constexpr int LIST_J = PASS_T * LIST_T + 4;      // 804 words: = 4 (mod 32)
+constexpr size_t DL_SMEM = (size_t)LT_ROWS * 8 * (sizeof(float4) + sizeof(float2)) + (size_t)LT_SLOTS * sizeof(float2) +
+                           (size_t)GL * LIST_J * 4 + (size_t)NB_THREADS * 2;
+constexpr size_t DL_SMEM_AKINCI = DL_SMEM + (size_t)LT_SLOTS * sizeof(int);
+
+template <bool AKINCI>
+__global__ void __launch_bounds__(NB_THREADS, 3)
+k_density_list(SimParams sp, const int* __restrict__ cell_end, const int2* __restrict__ items,
+               StepCounters* __restrict__ ctr, int pool_rows_cap, int all_to_fallback,
+               const float4* __restrict__ P, float4* __restrict__ V, const float4* __restrict__ Q,
+               float4* __restrict__ D, float* __restrict__ S, int* __restrict__ ncount,
+               uint32_t* __restrict__ Lg, int* __restrict__ item_row, unsigned char* __restrict__ flags,
+               int* __restrict__ fb_d, int* __restrict__ fb_f) {
+    extern __shared__ float4 dyn_smem[];
+    float4* FXY = dyn_smem;
+    float2* FZ = reinterpret_cast<float2*>(FXY + LT_ROWS * 8);
+    float2* GXY = FZ + LT_ROWS * 8;
+    unsigned char* L = reinterpret_cast<unsigned char*>(GXY + LT_SLOTS);
+    unsigned short* LC = reinterpret_cast<unsigned short*>(L + GL * LIST_J * 4);     // entries per stream: nA | nB << 8
+    int* GM = reinterpret_cast<int*>(LC + NB_THREADS);
+    __shared__ CellRanges R;
+    __shared__ int s_slot, s_over;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float cut_wide = sp.d2_cut * 1.000001f;          // superset filter; the drain applies the exact test
+    const float2 one2 = make_float2(sp.one, sp.one);       // see the drain: keeps ptxas from contracting the exact sum
+    // ---- filter arrangement: lane jF = warp, target tF = lane
+    const uint32_t fFXY = smem_u32(FXY) + 16u * warp, fFZ = smem_u32(FZ) + 8u * warp;
+    const uint32_t fL = smem_u32(L) + 4u * (LIST_J * warp + LIST_T * lane);
+    // a row-2k candidate goes to byte 2n + offA of the list, a row-2k+1 candidate to byte 2n + offB: the FIRST
+    // entry of every byte pair has the parity of the target's drain group (target & 1)
+    const uint32_t fA = fL + (lane & 1u), fB = fL + 1u - (lane & 1u);
+    // ---- drain arrangement: target tid / 8, lane j = tid % 8
+    const int j = tid & (GL - 1), tD = tid >> 3;
+    const uint32_t c1 = tD & 1u;                           // parity of my group: which stream I consume first
+    const uint32_t sG = smem_u32(GXY) + 8u * j, sGM = smem_u32(GM) + 4u * j;
+    const uint32_t sL = smem_u32(L) + 4u * (LIST_J * j + LIST_T * tD);
+    const uint32_t offA = c1, offB = 1u - c1;
+    // z of row m: FZ word 2 (8 (m >> 1) + j) + (m & 1)  =  byte 32 m + 8 j - 28 (m & 1)
+    const uint32_t zb1 = smem_u32(FZ) + 8u * j - 28u * c1, zb2 = smem_u32(FZ) + 8u * j - 28u * (1u - c1);
+    // the two dummy rows are FAR in every array, for good
+    if (tid < 16) GXY[8 * M_DUMMY + tid] = make_float2(FAR, FAR);
+    if (tid < 8) { FXY[8 * (LT_ROWS - 1) + tid] = make_float4(-FAR, -FAR, -FAR, -FAR); FZ[8 * (LT_ROWS - 1) + tid] = make_float2(-FAR, -FAR); }
+    if (AKINCI && tid < 16) GM[8 * M_DUMMY + tid] = MAT_FLUID;
+
+    for (;;) {
+        const int it = next_item(&ctr->work_d, &s_slot);
+        if (it >= ctr->n_items) break;
+        ItemGeom G;
+        item_setup(sp, cell_end, items[it], R, G);
+        if (G.total > LT_CAP || all_to_fallback) {          // a candidate's row must fit one byte
+            if (tid == 0) {
+                flags[it] = 2;
+                fb_d[atomicAdd(&ctr->n_fb_d, 1)] = it;
+                fb_f[atomicAdd(&ctr->n_fb_f, 1)] = it;
+            }
+            continue;
+        }
+        const bool own = G.c >= sp.own_key_lo && G.c < sp.own_key_hi;   // ghost cells get no force walk
+        const int npass = (G.nT + PASS_T - 1) / PASS_T;
+        if (tid == 0) s_over = 0;
+        // a ghost cell whose density does not depend on its neighbours (reference modes) skips the walk
+        const int walk_total = (own || sp.ghost_walk) ? G.total : 0;
+        // ---- stage the tile: rows of 16 candidates, padded with FAR to a whole filter chunk -------------
+        const int nrow2 = ((walk_total + 15) / 16 + FCHUNK - 1) / FCHUNK * FCHUNK;      // row pairs (k) staged
+        for (int p = tid; p < nrow2 * 8; p += NB_THREADS) {
+            const int sa = 16 * (p >> 3) + (p & 7), sb = sa + 8;      // slots (rows 2k and 2k+1, lane p & 7)
+            const int ea = slot_to_cand(sa), eb = slot_to_cand(sb);
+            float4 a = make_float4(FAR, FAR, FAR, 0.f), b = a;
+            int ma = MAT_FLUID, mb = MAT_FLUID;
+            if (ea < walk_total) {
+                const int g = tile_to_global(R, ea);
+                a = P[g];
+                if (AKINCI) ma = __float_as_int(Q[g].z);
+            }
+            if (eb < walk_total) {
+                const int g = tile_to_global(R, eb);
+                b = P[g];
+                if (AKINCI) mb = __float_as_int(Q[g].z);
+            }
+            TISPH_CHECK(sb < LT_SLOTS && p < LT_ROWS * 8);
+            FXY[p] = make_float4(-a.x, -b.x, -a.y, -b.y);
+            FZ[p] = make_float2(-a.z, -b.z);
+            GXY[sa] = make_float2(a.x, a.y);
+            GXY[sb] = make_float2(b.x, b.y);
+            if (AKINCI) { GM[sa] = ma; GM[sb] = mb; }
+        }
+        __syncthreads();
+        const int self_lo = R.gb[4], self_len = R.off[5] - R.off[4];
+        bool redo = false;
+
+        for (int pass = 0; pass < npass; ++pass) {
+            // ======== FILTER: my target against the candidates of lane `warp` ==============================
+            int ovf = 0;
+            {
+                const int tf = pass * PASS_T + lane;
+                const float4 pf = tf < G.nT ? P[G.i0 + tf] : make_float4(-FAR, -FAR, -FAR, 0.f);
+                const float2 xi2 = make_float2(pf.x, pf.x), yi2 = make_float2(pf.y, pf.y), zi2 = make_float2(pf.z, pf.z);
+                uint32_t pA = fA, pB = fB;                     // next free byte of the two pending streams
+                for (int k0 = 0; k0 < nrow2; k0 += FCHUNK) {
+                    // loads are issued four row pairs ahead of their use
+#pragma unroll
+                    for (int b4 = 0; b4 < FCHUNK; b4 += 4) {
+                        float4 c[4];
+                        float2 cz[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            c[u] = lds_f32x4(fFXY + 128u * (k0 + b4 + u));
+                            cz[u] = lds_f32x2(fFZ + 64u * (k0 + b4 + u));
+                        }
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const float2 dx = __fadd2_rn(xi2, make_float2(c[u].x, c[u].y));
+                            const float2 dy = __fadd2_rn(yi2, make_float2(c[u].z, c[u].w));
+                            const float2 dz = __fadd2_rn(zi2, cz[u]);
+                            const float2 s = __ffma2_rn(dz, dz, __ffma2_rn(dy, dy, __fmul2_rn(dx, dx)));
+                            const uint32_t m = 2u * (k0 + b4 + u);
+                            TISPH_CHECK(pA - fL < 2u * LCAP2 + 2u && pB - fL < 2u * LCAP2 + 2u);
+                            if (s.x < cut_wide) { sts_u8(pA, m); pA += 2u; }
+                            if (s.y < cut_wide) { sts_u8(pB, m + 1u); pB += 2u; }
+                        }
+                    }
+                    // a stream that could overflow with the next chunk: the whole item goes to the fallback kernels
+                    if (max(pA - fA, pB - fB) > 2u * (LCAP2 - FCHUNK)) { ovf = 1; break; }
+                }
+                LC[tid] = (unsigned short)(((pA - fA) >> 1) | (((pB - fB) >> 1) << 8));
+            }
+            if (__syncthreads_or(ovf)) { redo = true; break; }
+            // ======== DRAIN: target tid / 8, lane tid % 8 ====================================================
+            const int t_local = pass * PASS_T + tD;
+            const int i = G.i0 + t_local;
+            const bool active = t_local < G.nT;
+            const float4 pi = active ? P[i] : make_float4(-FAR, -FAR, -FAR, 0.f);
+            // my own slot in the tile, if this lane owns it
+            const int self_t = (active && walk_total > 0 && i >= self_lo && i < self_lo + self_len) ? R.off[4] + (i - self_lo) : -1;
+            const int self_s = self_t >= 0 ? cand_to_slot(self_t) : -1;
+            float2 wsum2 = make_float2(0.f, 0.f);
+            float wbsum = 0.f;
+            int cnt = 0;
+            // the filter thread of (target tD, lane j) was thread 32 j + tD
+            const uint32_t nab = LC[32 * j + tD];
+            const uint32_t nA = nab & 0xffu, nB = nab >> 8;
+            if (self_s >= 0 && (self_s & 7) == j) {
+                // p_i != p_j (partice_systemv4.py:344): the target itself passed the filter (d2 = 0).  Its stream
+                // is ascending, so a binary search finds the entry; the stream's dummy row takes its place.
+                const uint32_t ms = (uint32_t)self_s >> 3;
+                const uint32_t sb = sL + ((ms & 1u) ? offB : offA);
+                uint32_t lo = 0, hi = (ms & 1u) ? nB : nA;
+                while (lo < hi) {
+                    const uint32_t mid = (lo + hi) >> 1;
+                    if (lds_u8(sb + 2u * mid) < ms) lo = mid + 1u; else hi = mid;
+                }
+                TISPH_CHECK(lo < ((ms & 1u) ? nB : nA) && lds_u8(sb + 2u * lo) == ms);
+                sts_u8(sb + 2u * lo, M_DUMMY + (ms & 1u));
+            }
+            // pad both streams with their dummy row to the longest list of the warp (a whole number of words),
+            // then one (first, second) pair of entries per iteration, branch-free
+            const uint32_t n2 = (2u * max(nA, nB) + 2u) & ~3u;                  // 2 x pairs I hand to the force walk
+            const uint32_t nmax = __reduce_max_sync(0xffffffffu, n2);
+            for (uint32_t k = 2u * nA; k < nmax; k += 2u) sts_u8(sL + offA + k, M_DUMMY);
+            for (uint32_t k = 2u * nB; k < nmax; k += 2u) sts_u8(sL + offB + k, M_DUMMY + 1);
+            for (uint32_t k2 = 0; k2 < nmax; k2 += 2u) {
+                const uint32_t w = lds_u16(sL + k2);
+                const uint32_t m1 = w & 0xffu, m2 = w >> 8;
+                TISPH_CHECK((m1 & 1u) == c1 && (m2 & 1u) == 1u - c1 && k2 < 2u * LCAP2 + 4u);
+                const float2 xy1 = lds_f32x2(sG + 64u * m1);
+                const float nz1 = lds_f32(zb1 + 32u * m1);
+                const float2 xy2 = lds_f32x2(sG + 64u * m2);
+                const float nz2 = lds_f32(zb2 + 32u * m2);
+                const float2 dx = make_float2(pi.x - xy1.x, pi.x - xy2.x);
+                const float2 dy = make_float2(pi.y - xy1.y, pi.y - xy2.y);
+                const float2 dz = make_float2(pi.z + nz1, pi.z + nz2);
+                // d2 in the reference's evaluation order with every product rounded (dist2_exact, two at a
+                // time).  ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even with explicit .rn, so the
+                // sums are written as fma(y2, 1, x2) with a run-time 1: exact, and nothing left to contract.
+                const float2 d2 = __ffma2_rn(__fmul2_rn(dz, dz), one2, __ffma2_rn(__fmul2_rn(dy, dy), one2, __fmul2_rn(dx, dx)));
+                const float2 rinv = make_float2(rsqrt_approx(fmaxf(d2.x, 1e-30f)), rsqrt_approx(fmaxf(d2.y, 1e-30f)));
+                // r = d2 / sqrt(d2) with one Newton step on top of MUFU.RSQ: the density sum feeds p = B (x^7 - 1),
+                // which multiplies its relative error by 7 and more, so r is kept to ~1 ulp here
+                const float2 r0 = __fmul2_rn(d2, rinv);
+                const float2 e = __ffma2_rn(__fmul2_rn(r0, make_float2(-1.0f, -1.0f)), rinv, make_float2(1.0f, 1.0f));
+                const float2 r = __ffma2_rn(__fmul2_rn(r0, make_float2(0.5f, 0.5f)), e, r0);
+                float2 q = __fmul2_rn(r, make_float2(sp.inv_h, sp.inv_h));
+                q.x = fminf(q.x, 1.0f); q.y = fminf(q.y, 1.0f);
+                // cubic spline, branch-free:  W/k = 2 (1-q)^3 - 8 max(1/2 - q, 0)^3   (sph_basev2.py:19-36)
+                const float2 nf = __fadd2_rn(q, make_float2(-1.0f, -1.0f));
+                float2 g = __ffma2_rn(q, make_float2(-1.0f, -1.0f), make_float2(0.5f, 0.5f));
+                g.x = fmaxf(g.x, 0.f); g.y = fmaxf(g.y, 0.f);
+                const float2 nf3 = __fmul2_rn(__fmul2_rn(nf, nf), nf);
+                const float2 g3 = __fmul2_rn(__fmul2_rn(g, g), g);
+                if (AKINCI) {
+                    const float2 w2 = __ffma2_rn(g3, make_float2(-8.0f, -8.0f), __fmul2_rn(nf3, make_float2(-2.0f, -2.0f)));
+                    wsum2 = __fadd2_rn(wsum2, w2);
+                    wbsum += (int)lds_u32(sGM + 32u * m1) == MAT_BOUNDARY ? w2.x : 0.f;
+                    wbsum += (int)lds_u32(sGM + 32u * m2) == MAT_BOUNDARY ? w2.y : 0.f;
+                } else {
+                    wsum2 = __ffma2_rn(nf3, make_float2(-2.0f, -2.0f), wsum2);
+                    wsum2 = __ffma2_rn(g3, make_float2(-8.0f, -8.0f), wsum2);
+                }
+                if (d2.x < sp.d2_cut) ++cnt;
+                if (d2.y < sp.d2_cut) ++cnt;
+            }
+            // ---- hand my pairs to the force walk: the warp reserves a count row and the rows of its longest
+            //      lane (rows of 32 words), then copies whole words of (first, second, first, second) entries
+            if (own) {
+                const int nw = (int)(n2 >> 2);
+                const int rows = __reduce_max_sync(0xffffffffu, nw) + 1;
+                int row = 0;
+                if (lane == 0) {
+                    row = atomicAdd(&ctr->pool_rows, rows);
+                    if (row + rows > pool_rows_cap) { row = -1; s_over = 1; }   // pool exhausted: fallback force kernel
+                    item_row[(2 * it + pass) * 8 + warp] = row;
+                }
+                row = __shfl_sync(0xffffffffu, row, 0);
+                if (row >= 0) {
+                    uint32_t* gp = Lg + (size_t)row * 32 + lane;
+                    *gp = (uint32_t)nw;                        // count row, in words
+                    for (int q4 = 0; q4 < nw; ++q4) {
+                        gp += 32;
+                        TISPH_CHECK(row + 1 + q4 < pool_rows_cap);
+                        *gp = lds_u32(sL + 4u * q4);
+                    }
+                }
+            }
+            float wsum = wsum2.x + wsum2.y;
+#pragma unroll
+            for (int o = 1; o < GL; o <<= 1) {
+                wsum += __shfl_xor_sync(0xffffffffu, wsum, o);
+                cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+                if (AKINCI) wbsum += __shfl_xor_sync(0xffffffffu, wbsum, o);
+            }
+            if (j == 0 && active)
+                density_epilogue(sp, i, pi.w, __float_as_int(Q[i].z), wsum, wbsum, cnt, V, Q, D, S, ncount);
+            __syncthreads();                                   // the lists are free for the next pass; s_over is complete
+        }
+        if (tid == 0) {
+            if (redo) {                                        // a pending list would have overflowed: both walks fall back
+                flags[it] = 2;
+                fb_d[atomicAdd(&ctr->n_fb_d, 1)] = it;
+                fb_f[atomicAdd(&ctr->n_fb_f, 1)] = it;
+            } else {
+                flags[it] = (unsigned char)s_over;
+                if (s_over && own) fb_f[atomicAdd(&ctr->n_fb_f, 1)] = it;
+            }
+        }
+    }
+}
+
+// =======================================================================================
+// Walk 2: forces + advect + walls.  Tile = five planes of LT_SLOTS 8-byte (4-byte) slots:
+//   P01 {x,y}   P23 {z,psi}   V01 {vx,vy}   V23 {vz,rho_raw}   PR p/rho_c^2
+//   psi = +mass_j (fluid j) / -volume_j (boundary j)
+// =======================================================================================
+constexpr uint32_t PLANE_B = (uint32_t)LT_SLOTS * sizeof(float2);
+constexpr size_t FL_SMEM = (size_t)LT_SLOTS * (4 * sizeof(float2) + sizeof(float));
+
+struct ForceAcc2 { float2 anx, any, anz, apx, apy, apz; };
+
+// Branch-free evaluation of two neighbours (wcsphv2.py:56-80 ; sph_basev2.py:64-78).  The self pair and
+// coincident particles give exactly zero (x_ij = 0 and gradW = 0 for r <= 1e-5, sph_basev2.py:53);
+// entries outside the cutoff (filter band, list padding) have q clamped to 1, where W and gradW vanish.
+//   dW/dq / (6k) = 4 max(1/2 - q, 0)^2 - (1-q)^2     (sph_basev2.py:53-60)
+template <bool HAS_BOUNDARY>
+__device__ __forceinline__ void pair_force2(const SimParams& sp, float nkdw_h, float4 pi, float4 vi, float coh_kw,
+                                            float rho_i, float pr_i, float nub_i, float2 xy1, float2 zp1, float2 vxy1,
+                                            float2 vzr1, float pr1, float2 xy2, float2 zp2, float2 vxy2, float2 vzr2,
+                                            float pr2, ForceAcc2& A) {
+    const float2 dx = make_float2(pi.x - xy1.x, pi.x - xy2.x);
+    const float2 dy = make_float2(pi.y - xy1.y, pi.y - xy2.y);
+    const float2 dz = make_float2(pi.z - zp1.x, pi.z - zp2.x);
+    const float2 d2 = __ffma2_rn(dz, dz, __ffma2_rn(dy, dy, __fmul2_rn(dx, dx)));
+    const float2 rinv = make_float2(rsqrt_approx(fmaxf(d2.x, 1e-30f)), rsqrt_approx(fmaxf(d2.y, 1e-30f)));
+    const float2 r = __fmul2_rn(d2, rinv);
+    float2 q = __fmul2_rn(r, make_float2(sp.inv_h, sp.inv_h));
+    q.x = fminf(q.x, 1.0f); q.y = fminf(q.y, 1.0f);                  // beyond the support W = gradW = 0: no mask needed
+    const float2 nf = __fadd2_rn(q, make_float2(-1.0f, -1.0f));
+    float2 g = __ffma2_rn(q, make_float2(-1.0f, -1.0f), make_float2(0.5f, 0.5f));
+    g.x = fmaxf(g.x, 0.f); g.y = fmaxf(g.y, 0.f);
+    const float2 f2 = __fmul2_rn(nf, nf), g2 = __fmul2_rn(g, g);
+    const float2 ndw = __ffma2_rn(g2, make_float2(-4.0f, -4.0f), f2);                 // -dW/dq / (6k)
+    float2 gfac = __fmul2_rn(__fmul2_rn(ndw, rinv), make_float2(nkdw_h, nkdw_h));    // gradW = gfac * x_ij
+    gfac.x = r.x > 1e-5f ? gfac.x : 0.f;
+    gfac.y = r.y > 1e-5f ? gfac.y : 0.f;
+    const float2 dvx = make_float2(vi.x - vxy1.x, vi.x - vxy2.x);
+    const float2 dvy = make_float2(vi.y - vxy1.y, vi.y - vxy2.y);
+    const float2 dvz = make_float2(vi.z - vzr1.x, vi.z - vzr2.x);
+    float2 dot = __ffma2_rn(dvz, dz, __ffma2_rn(dvy, dy, __fmul2_rn(dvx, dx)));
+    dot.x = fminf(dot.x, 0.f); dot.y = fminf(dot.y, 0.f);
+    // min(v.x, 0) / (d2 + 0.01 h^2) / (rho_i + rho_j) with one reciprocal (wcsphv2.py:69-73)
+    const float2 d2e = __fadd2_rn(d2, make_float2(sp.eps_h2, sp.eps_h2));
+    const float2 rs = make_float2(rho_i + vzr1.y, rho_i + vzr2.y);
+    const float2 den = __fmul2_rn(d2e, rs);
+    const float2 mnr = __fmul2_rn(dot, make_float2(rcp_approx(den.x), rcp_approx(den.y)));
+    const float2 t = __fmul2_rn(mnr, gfac);
+    const float2 nf3 = __fmul2_rn(f2, nf), g3 = __fmul2_rn(g2, g);
+    // coh_i k_w W/k = coh_kw (-2 nf^3 - 8 g^3)
+    const float2 cw = __fmul2_rn(__ffma2_rn(g3, make_float2(-8.0f, -8.0f), __fmul2_rn(nf3, make_float2(-2.0f, -2.0f))),
+                                 make_float2(coh_kw, coh_kw));
+    const float2 u = __ffma2_rn(t, make_float2(-sp.visc_fluid_c, -sp.visc_fluid_c), cw);   // :64 + :72-73
+    const float2 ps = __fmul2_rn(__fadd2_rn(make_float2(pr1, pr2), make_float2(pr_i, pr_i)), gfac);
+    float2 cn = make_float2(zp1.y * u.x, zp2.y * u.y);                               // psi (coh_i W - nu mn gradW)
+    float2 cp = make_float2(-zp1.y * ps.x, -zp2.y * ps.y);                           // sph_basev2.py:71-73
+    if (HAS_BOUNDARY) {
+        const float2 mnb = __fmul2_rn(t, rs);                                        // min(v.x,0)/(d2+eps) gfac
+        const float cb = sp.ps_density0 * nub_i, pb = sp.rho0 * pr_i;
+        // boundary j: psi = -volume_j                     wcsphv2.py:78-80 ; sph_basev2.py:75
+        cn.x = zp1.y > 0.f ? cn.x : cb * zp1.y * mnb.x;
+        cn.y = zp2.y > 0.f ? cn.y : cb * zp2.y * mnb.y;
+        cp.x = zp1.y > 0.f ? cp.x : pb * zp1.y * gfac.x;
+        cp.y = zp2.y > 0.f ? cp.y : pb * zp2.y * gfac.y;
+    }
+    A.anx = __ffma2_rn(cn, dx, A.anx); A.any = __ffma2_rn(cn, dy, A.any); A.anz = __ffma2_rn(cn, dz, A.anz);
+    A.apx = __ffma2_rn(cp, dx, A.apx); A.apy = __ffma2_rn(cp, dy, A.apy); A.apz = __ffma2_rn(cp, dz, A.apz);
+}
+
+template <bool HAS_BOUNDARY>
+__global__ void __launch_bounds__(NB_THREADS, 3)
+k_force_list(SimParams sp, const int* __restrict__ cell_end, const int2* __restrict__ items,
+             StepCounters* __restrict__ ctr, const float4* __restrict__ Pin,
+             const float4* __restrict__ Vin, const float4* __restrict__ Qin,
+             const float4* __restrict__ D, float4* __restrict__ Pout, float4* __restrict__ Vout,
+             float4* __restrict__ Qout, float4* __restrict__ dvel, float4* __restrict__ a_np_out,
+             float4* __restrict__ a_p_out, const uint32_t* __restrict__ Lg,
+             const int* __restrict__ item_row, const unsigned char* __restrict__ flags) {
+    extern __shared__ float4 dyn_smem[];
+    float2* P01 = reinterpret_cast<float2*>(dyn_smem);
+    float2* P23 = P01 + LT_SLOTS;
+    float2* V01 = P23 + LT_SLOTS;
+    float2* V23 = V01 + LT_SLOTS;
+    float* PR = reinterpret_cast<float*>(V23 + LT_SLOTS);
+    __shared__ CellRanges R;
+    __shared__ int s_slot;
+    const int tid = threadIdx.x;
+    const int j = tid & (GL - 1);
+    const uint32_t sP = smem_u32(P01) + 8u * j, sR = smem_u32(PR) + 4u * j;
+    const float nkdw_h = -sp.k_dw * sp.inv_h;
+    if (tid < 16) {                                         // the two dummy rows: FAR away, for good
+        const int s = 8 * M_DUMMY + tid;
+        P01[s] = make_float2(FAR, FAR); P23[s] = make_float2(FAR, 1.f);
+        V01[s] = make_float2(0.f, 0.f); V23[s] = make_float2(0.f, 1.f);
+        PR[s] = 0.f;
+    }
+
+    for (;;) {
+        const int it = next_item(&ctr->work_f, &s_slot);
+        if (it >= ctr->n_items) break;
+        if (flags[it]) continue;                         // handled by k_force_fb
+        if (items[it].x < sp.own_key_lo || items[it].x >= sp.own_key_hi) continue;   // ghost cell: not advanced here
+        ItemGeom G;
+        item_setup(sp, cell_end, items[it], R, G);
+        TISPH_CHECK(G.total <= LT_CAP);
+        const int npass = (G.nT + PASS_T - 1) / PASS_T;
+        // ---- stage the tile: candidate e in slot cand_to_slot(e); two candidates per thread and round,
+        //      all eight loads in flight before the first store
+        for (int e0 = tid; e0 < G.total; e0 += 2 * NB_THREADS) {
+            const int e1 = e0 + NB_THREADS;
+            const bool two = e1 < G.total;
+            const int g0 = tile_to_global(R, e0), g1 = two ? tile_to_global(R, e1) : g0;
+            const float4 p0 = Pin[g0], v0 = Vin[g0], d0 = D[g0], q0 = Qin[g0];
+            const float4 p1 = Pin[g1], v1 = Vin[g1], d1 = D[g1], q1 = Qin[g1];
+            {
+                const float psi = __float_as_int(q0.z) != MAT_FLUID ? -v0.w : p0.w;
+                const int sl = cand_to_slot(e0);
+                P01[sl] = make_float2(p0.x, p0.y); P23[sl] = make_float2(p0.z, psi);
+                V01[sl] = make_float2(v0.x, v0.y); V23[sl] = make_float2(v0.z, d0.x);
+                PR[sl] = d0.y;
+            }
+            if (two) {
+                const float psi = __float_as_int(q1.z) != MAT_FLUID ? -v1.w : p1.w;
+                const int sl = cand_to_slot(e1);
+                P01[sl] = make_float2(p1.x, p1.y); P23[sl] = make_float2(p1.z, psi);
+                V01[sl] = make_float2(v1.x, v1.y); V23[sl] = make_float2(v1.z, d1.x);
+                PR[sl] = d1.y;
+            }
+        }
+        __syncthreads();
+        for (int pass = 0; pass < npass; ++pass) {
+            const int t_local = pass * PASS_T + (tid >> 3);
+            const int i = G.i0 + t_local;
+            const bool active = t_local < G.nT;
+            const float4 pi = active ? Pin[i] : make_float4(-FAR, -FAR, -FAR, 1.f);
+            const float4 vi = active ? Vin[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float4 di = active ? D[i] : make_float4(1.f, 0.f, 1.f, 0.f);
+            const float4 qi = active ? Qin[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+            const bool walker = active && __float_as_int(qi.z) == MAT_FLUID;
+            const float coh_kw = 0.01f / pi.w * sp.k_w;                // wcsphv2.py:64 (x the kernel normalisation)
+            const float rho_i = di.x, pr_i = di.y;
+            const float nub_i = sp.visc_bound_c / (2.0f * rho_i);     // wcsphv2.py:76
+            ForceAcc2 A;
+            A.anx = A.any = A.anz = A.apx = A.apy = A.apz = make_float2(0.f, 0.f);
+            const int row = item_row[(2 * it + pass) * 8 + (tid >> 5)];     // my warp's rows of the list pool
+            TISPH_CHECK(row >= 0);
+            const uint32_t* gl = Lg + (size_t)row * 32 + (tid & 31);
+            const int nw = walker ? (int)gl[0] : 0;                   // words of 4 entries (count row)
+            TISPH_CHECK(nw >= 0 && nw <= LCAP2 / 2);
+            gl += 32;
+            // list words are fetched three ahead of their use (a word is ~190 instructions of work)
+            uint32_t w0 = nw > 0 ? gl[0] : 0u, w1 = nw > 1 ? gl[32] : 0u, w2 = nw > 2 ? gl[64] : 0u;
+            for (int k = 0; k < nw; ++k) {
+                const uint32_t cur = w0;
+                w0 = w1; w1 = w2;
+                if (k + 3 < nw) w2 = gl[(size_t)(k + 3) * 32];
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const uint32_t m1 = (cur >> (16 * h)) & 0xffu, m2 = (cur >> (16 * h + 8)) & 0xffu;
+                    const uint32_t a1 = sP + 64u * m1, a2 = sP + 64u * m2;
+                    const float2 xy1 = lds_f32x2(a1), zp1 = lds_f32x2(a1 + PLANE_B);
+                    const float2 vxy1 = lds_f32x2(a1 + 2u * PLANE_B), vzr1 = lds_f32x2(a1 + 3u * PLANE_B);
+                    const float pr1 = lds_f32(sR + 32u * m1);
+                    const float2 xy2 = lds_f32x2(a2), zp2 = lds_f32x2(a2 + PLANE_B);
+                    const float2 vxy2 = lds_f32x2(a2 + 2u * PLANE_B), vzr2 = lds_f32x2(a2 + 3u * PLANE_B);
+                    const float pr2 = lds_f32(sR + 32u * m2);
+                    pair_force2<HAS_BOUNDARY>(sp, nkdw_h, pi, vi, coh_kw, rho_i, pr_i, nub_i, xy1, zp1, vxy1, vzr1, pr1,
+                                              xy2, zp2, vxy2, vzr2, pr2, A);
+                }
+            }
+            float a6[6] = {A.anx.x + A.anx.y, A.any.x + A.any.y, A.anz.x + A.anz.y,
+                           A.apx.x + A.apx.y, A.apy.x + A.apy.y, A.apz.x + A.apz.y};
+#pragma unroll
+            for (int o = 1; o < GL; o <<= 1)
+#pragma unroll
+                for (int c = 0; c < 6; ++c) a6[c] += __shfl_xor_sync(0xffffffffu, a6[c], o);
+            if (j == 0 && active)
+                force_epilogue(sp, i, walker, pi, vi, di, qi, a6[0], a6[1], a6[2], a6[3], a6[4], a6[5],
+                               Pout, Vout, Qout, dvel, a_np_out, a_p_out);
+        }
+    }
+}
+
+}  // namespace tisph

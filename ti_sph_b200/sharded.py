@@ -413,6 +413,20 @@ class ShardedSim:
         total = sum(self.comm.all_gather_objects(self.owned_plane_counts()))
         return self.apply_histogram(total)
 
+    def close(self):
+        """release the engine, the peer mappings and (rank 0: unlink) the shared-memory count segment"""
+        if self._shm is not None:
+            self._shm.close()
+            self._shm = None
+        eng, self.engine = self.engine, None
+        if eng is not None:
+            try:
+                eng.sync()
+                if self.p2p:
+                    eng.shard_ipc_disconnect()
+            finally:
+                eng.close()
+
     # -- state -------------------------------------------------------------------------------
     def save_state(self):
         self.engine.save_state()
