@@ -10,8 +10,13 @@ CUDA, see include/tisph.h):
   add_particles kernel (:171-204)                    tisph_add_particles
   update() = update_gird_id + scan + resort (:251)   tisph_stage_run(TISPH_STAGE_UPDATE)
   for_all_neighbors (:331-345)                       inside the density / force kernels
+  update_gird_id / prefix_sum_executor.run / resort  TISPH_STAGE_UPDATE_BIN / _SCAN / _SORT
   dump(), copy_to_numpy(_nd) (:279-307)              tisph_download
   load_rigid_body via trimesh (:259-277)             ti_sph_b200.mesh (OBJ + voxeliser)
+
+A script may drive a step kernel by kernel, as the reference allows (update_gird_id(),
+prefix_sum_executor.run(...), resort(), then the solver's compute_* / advert / enforce_boundary):
+between those calls every field view shows what the reference's field holds at that point.
 """
 from functools import reduce
 
@@ -65,6 +70,11 @@ class ParticleSystemV4:
                           ("grid_ids", K.F_GRID_IDS),
                           ("grid_particles_num", K.F_GRID_PARTICLES_NUM)):
             setattr(self, name, FieldView(self, fid, name))
+        self.grid_particles_num_temp = FieldView(self, K.F_CELL_COUNT, "grid_particles_num_temp")
+        self.paritcle_index_temp = FieldView(self, K.F_PARTICLE_INDEX, "paritcle_index_temp")   # needs P_DIAGNOSTICS
+        self.prefix_sum_executor = _PrefixSumExecutor(self)          # ti.algorithms.PrefixSumExecutor, :62
+        self._overrides = {}         # field name -> library field, while a step is driven kernel by kernel
+        self._kernel_stage = 0       # ... and how far that step got (core/sph/sph_basev2.py)
         self.m = ConstantField(self, "m")            # allocated, sorted along and never written by the reference (:39)
         self.add_fluid_and_rigid()
         if self.engine.particle_num != self.particle_max_num:
@@ -139,9 +149,35 @@ class ParticleSystemV4:
                                   color[:num])
 
     # ---- per-step --------------------------------------------------------------------
+    def _field_override(self, name, field):
+        return self._overrides.get(name, field)
+
+    def update_gird_id(self):
+        """cell key per particle + histogram (partice_systemv4.py:206-215); ps.grid_ids then holds the keys
+        in the particles' current order and ps.grid_particles_num the counts"""
+        self._overrides.clear()
+        self._kernel_stage = 0
+        self.engine.stage(K.STAGE_UPDATE_BIN)
+
+    def resort(self):
+        """stable counting-sort rank + reorder of every per-particle array (partice_systemv4.py:217-249)"""
+        self.engine.stage(K.STAGE_UPDATE_SORT)
+
     def update(self):
         """bin + prefix scan + stable counting sort + reorder (partice_systemv4.py:251-256)"""
-        self.engine.stage(K.STAGE_UPDATE)
+        self.update_gird_id()
+        self.prefix_sum_executor.run(self.grid_particles_num)
+        self.resort()
+
+    def copy_to_numpy(self, np_arr, src_arr):
+        """partice_systemv4.py:298-301: np_arr[i] = src_arr[i] for the particles in use"""
+        n = self.engine.particle_num
+        np_arr[:n] = src_arr.to_numpy()[:n]
+
+    def copy_to_numpy_nd(self, np_arr, src_arr):
+        """partice_systemv4.py:303-307"""
+        n = self.engine.particle_num
+        np_arr[:n, :self.dim] = src_arr.to_numpy()[:n]
 
     def dump(self, out=None):
         """dict of host copies like the reference (:279-296). `out` (extension) may hold
@@ -165,3 +201,16 @@ class ParticleSystemV4:
 
     def get_flatten_grid_index(self, pos):
         return self.flatten_grid_index(self.pos_to_index(pos))
+
+
+class _PrefixSumExecutor:
+    """ti.algorithms.PrefixSumExecutor as ParticleSystemV4 uses it (partice_systemv4.py:62,255): an
+    in-place inclusive scan of ps.grid_particles_num."""
+
+    def __init__(self, ps):
+        self._ps = ps
+
+    def run(self, field):
+        if field is not self._ps.grid_particles_num:
+            raise ValueError("the executor of a ParticleSystemV4 scans ps.grid_particles_num")
+        self._ps.engine.stage(K.STAGE_UPDATE_SCAN)

@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define TISPH_ABI_VERSION 1
+#define TISPH_ABI_VERSION 2
 
 typedef struct tisph_ctx tisph_ctx;
 
@@ -91,8 +91,15 @@ typedef enum tisph_field {
     TISPH_F_A_NONPRESSURE = 15, /* d_velocity after wcsphv2.py:93 (needs TISPH_P_DIAGNOSTICS) */
     TISPH_F_A_PRESSURE = 16,  /* sum added at wcsphv2.py:53 (needs TISPH_P_DIAGNOSTICS) */
     TISPH_F_CELL_COUNT = 17,  /* histogram before the scan, partice_systemv4.py:213  i32 [ncell] */
-    TISPH_F_NEIGHBORS = 18    /* gen-1 only: ps.particle_neighbors i32 [n][100], zero-filled beyond the
+    TISPH_F_NEIGHBORS = 18,   /* gen-1 only: ps.particle_neighbors i32 [n][100], zero-filled beyond the
                                  count (partice_system.py:102-121,213); counts = TISPH_F_NEIGHBOR_COUNT */
+    /* what the reference's fields hold BETWEEN its kernels (the drop-in classes map ps.x, ps.pressure ...
+       onto these while a step is driven kernel by kernel, as tests/golden/make_golden.py does) */
+    TISPH_F_X_IN = 19,        /* ps.x between resort() and advert(): the sorted, not yet advected positions */
+    TISPH_F_V_IN = 20,        /* ps.v, likewise */
+    TISPH_F_PRESSURE_STORED = 21, /* ps.pressure before compute_pressure_force: the previous step's, sorted along */
+    TISPH_F_PARTICLE_INDEX = 22   /* ps.paritcle_index_temp (partice_systemv4.py:219-224): sorted position of
+                                 every pre-sort particle   i32 [n]  (needs TISPH_P_DIAGNOSTICS) */
 } tisph_field;
 
 /* Stages of one step, for stage-by-stage parity tests (tisph_step runs them in order). */
@@ -101,8 +108,15 @@ typedef enum tisph_stage {
                                  (partice_systemv4.py:251-256) ; gen-1: ps.init() */
     TISPH_STAGE_DENSITY = 1,  /* compute_volume_of_boundary_particle + compute_densities +
                                  clamp/EOS (sph_basev2.py:195-201, wcsphv2.py:28-34,45-47) */
-    TISPH_STAGE_FORCE_ADVECT = 2 /* compute_non_pressure_force + compute_pressure_force +
+    TISPH_STAGE_FORCE_ADVECT = 2, /* compute_non_pressure_force + compute_pressure_force +
                                  advert + enforce_boundary (wcsphv2.py:83-100, sph_basev2.py:204) */
+    /* TISPH_STAGE_UPDATE in the reference's three calls (gen-2), to be issued in this order: */
+    TISPH_STAGE_UPDATE_BIN = 3,  /* ps.update_gird_id(): keys + histogram (partice_systemv4.py:206-215) */
+    TISPH_STAGE_UPDATE_SCAN = 4, /* ps.prefix_sum_executor.run(ps.grid_particles_num) (:62,255) */
+    TISPH_STAGE_UPDATE_SORT = 5, /* ps.resort() (:217-249) */
+    /* enforce_boundary() on its own (sph_basev2.py:204-208): after a TISPH_STAGE_FORCE_ADVECT that ran with
+       TISPH_P_SPLIT_WALLS = 1 and therefore stopped after advert() */
+    TISPH_STAGE_WALLS = 6
 } tisph_stage;
 
 typedef enum tisph_param {
@@ -122,11 +136,24 @@ typedef enum tisph_param {
     TISPH_P_STAT_FALLBACK_FORCE = 9,    /* ... plus items whose neighbour lists overflowed */
     TISPH_P_CFL = 10          /* extension: > 0 turns on a CFL step,
                                  dt = min(TISPH_P_DT, cfl * h / (c_s + max|v|)), evaluated before every step of
-                                 tisph_step; 0 (default) = the reference's fixed dt.  In a sharded run the
-                                 ranks must agree on dt themselves (ShardedSim does not turn this on). */
-    , TISPH_P_STAT_CHECK_FAILURES = 11 /* read-only: device-side bounds checks that failed so far, in libraries
+                                 tisph_step; 0 (default) = the reference's fixed dt.  Rejected (TISPH_ERR_INVALID) on a
+                                 sharded context: every rank would pick its own dt; ShardedSim.set_cfl max-reduces
+                                 TISPH_P_MAX_SPEED over the ranks and sets TISPH_P_DT instead. */
+    , TISPH_P_STAT_CHECK_FAILURES = 11, /* read-only: device-side bounds checks that failed so far, in libraries
                                  built with -DTISPH_CHECKS (count + first failing source line / 1e6);
                                  -1 when the checks are compiled out */
+    TISPH_P_SPLIT_WALLS = 12, /* 1: TISPH_STAGE_FORCE_ADVECT stops after advert(); the walls are applied by
+                                 TISPH_STAGE_WALLS (kernel-by-kernel drivers); 0 (default): fused */
+    TISPH_P_PHASE = 13,       /* read-only: 0 between steps, 1 after UPDATE, 2 after DENSITY;
+                                 + 10 (20) after UPDATE_BIN (UPDATE_SCAN) */
+    /* the solver attributes of the reference, assignable after construction like there */
+    TISPH_P_STIFFNESS = 14,   /* WCSPH(V2).stiffness, wcsphv2.py:11 */
+    TISPH_P_EXPONENT = 15,    /* WCSPH(V2).exponent,  wcsphv2.py:10 */
+    TISPH_P_VISCOSITY = 16,   /* SPHBase(V2).viscosity, sph_basev2.py:12 (the kernels' coefficients follow) */
+    TISPH_P_DENSITY0 = 17,    /* SPHBase(V2).density_0, sph_basev2.py:13 */
+    TISPH_P_GRAVITY_X = 18, TISPH_P_GRAVITY_Y = 19, TISPH_P_GRAVITY_Z = 20,   /* SPHBaseV2.g, sph_basev2.py:16 */
+    TISPH_P_MAX_SPEED = 21    /* read-only: max |v| over the fluid particles this context owns (synchronises);
+                                 a sharded run max-reduces it over the ranks to agree on a CFL step */
 } tisph_param;
 
 const char *tisph_last_error(void);

@@ -222,12 +222,14 @@ class Gen2Oracle:
                              _p(self.density), _p(self.pressure), _p(self.material),
                              _p(self.scan), _p(self.dvel), _p(self.a_pressure))
 
-    def force_magnitudes(self, density_pre):
+    def force_magnitudes(self, density_pre, pressure=None):
         """(sum |non-pressure term|, sum |pressure term|) per particle: the scale of the rounding error of
-        the two acceleration sums (test support; call after compute_pressure_force, before advert)."""
+        the two acceleration sums (test support; call after compute_pressure_force, before advert).
+        `pressure` replaces the pressure field (e.g. by its tolerance floor)."""
         mnp, mp = np.zeros(self.n, np.float32), np.zeros(self.n, np.float32)
+        pr = self.pressure if pressure is None else _f32(pressure)
         lib().ora_force_magnitudes(C.byref(self.cfg), self.n, _p(self.x), _p(self.v), _p(self.mass),
-                                   _p(self.volume), _p(_f32(density_pre)), _p(self.density), _p(self.pressure),
+                                   _p(self.volume), _p(_f32(density_pre)), _p(self.density), _p(pr),
                                    _p(self.material), _p(self.scan), _p(mnp), _p(mp))
         return mnp, mp
 
@@ -260,6 +262,10 @@ class Gen2Oracle:
             t.update(density=self.density.copy(), pressure=self.pressure.copy(),
                      a_pressure=self.a_pressure.copy(), d_velocity=self.dvel.copy())
             t["mag_nonpressure"], t["mag_pressure"] = self.force_magnitudes(t["density_pre"])
+            # p = B (x^7 - 1) cancels near x = 1: the tests allow |dp| <= rtol |p| + p_floor; the pressure sum
+            # inherits the same sum with p_floor in the place of p
+            t["p_floor"] = (50 * 8 * np.finfo(np.float32).eps * (self.density.astype(np.float64) / 1000.0) ** 7).astype(np.float32)
+            t["mag_pressure_floor"] = self.force_magnitudes(t["density_pre"], pressure=t["p_floor"])[1]
         self.advert()
         if trace:
             t.update(x_advected=self.x.copy(), v_advected=self.v.copy())
@@ -375,6 +381,10 @@ class Gen1Oracle:
         if trace:
             t.update(density=self.density.copy(), pressure=self.pressure.copy(),
                      d_velocity=self.dvel.copy())
+            t.update(self.force_magnitudes(self.x, self.v, t["density_pre"], self.density, self.pressure,
+                                           self.neighbors, self.neighbors_num))
+            t.update(a_pressure=(t["d_velocity"].astype(np.float64) - t["a_nonpressure"]).astype(np.float32),
+                     material=self.material.copy())
         L.ora_advect(c, n, _p(self.x), _p(self.v), _p(self.dvel), _p(self.material))
         if trace:
             t.update(x=self.x.copy(), v=self.v.copy())
@@ -383,3 +393,22 @@ class Gen1Oracle:
     def dump(self):
         return {"position": self.x.copy(), "velocity": self.v.copy(),
                 "material": self.material.copy(), "color": self.color.copy()}
+
+
+def _g1_force_magnitudes(self, x, v, density_pre, density, pressure, neighbors, neighbors_num):
+    """test support (see Gen2Oracle.force_magnitudes): magnitude sums of the gen-1 acceleration terms for
+    the given pre-advection state, and the same pressure sum with the tolerance floor of
+    p = B (x^7 - 1) in the place of p"""
+    n = len(x)
+    c = C.byref(self.cfg)
+    mnp, mp, mpf, scratch = (np.zeros(n, np.float32) for _ in range(4))
+    args = (_p(_f32(x)), _p(_f32(v)), _p(_f32(density_pre)), _p(_f32(density)))
+    tail = (_p(np.ascontiguousarray(self.material, np.int32)), _p(np.ascontiguousarray(neighbors, np.int32)),
+            _p(np.ascontiguousarray(neighbors_num, np.int32)))
+    lib().ora_g1_force_magnitudes(c, n, *args, _p(_f32(pressure)), *tail, _p(mnp), _p(mp))
+    p_floor = (50 * 8 * np.finfo(np.float32).eps * (np.asarray(density, np.float64) / 1000.0) ** 7).astype(np.float32)
+    lib().ora_g1_force_magnitudes(c, n, *args, _p(p_floor), *tail, _p(scratch), _p(mpf))
+    return {"mag_nonpressure": mnp, "mag_pressure": mp, "mag_pressure_floor": mpf}
+
+
+Gen1Oracle.force_magnitudes = _g1_force_magnitudes

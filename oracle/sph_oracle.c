@@ -602,6 +602,37 @@ void ora_g1_pressure_force(const ora_config *c, int n, const float *x, const flo
     }
 }
 
+/* Test support, gen-1 twin of ora_force_magnitudes: sums of the magnitudes of the terms that
+ * ora_g1_non_pressure (|g| + viscosity pairs) and ora_g1_pressure_force add up, in double. */
+void ora_g1_force_magnitudes(const ora_config *c, int n, const float *x, const float *v,
+                             const float *density_pre, const float *density, const float *pressure,
+                             const int32_t *material, const int32_t *neighbors,
+                             const int32_t *neighbors_num, float *mag_np, float *mag_p) {
+#pragma omp parallel for schedule(static)
+    for (int i = 0; i < n; ++i) {
+        mag_np[i] = 0.0f;
+        mag_p[i] = 0.0f;
+        if (material[i] != MAT_FLUID) continue;
+        double snp = fabs((double)c->g[1]), sp = 0.0;
+        for (int t = 0; t < neighbors_num[i]; ++t) {
+            int32_t j = neighbors[(size_t)i * c->max_neighbors + t];
+            float r[2] = {x[2 * (size_t)i] - x[2 * (size_t)j], x[2 * (size_t)i + 1] - x[2 * (size_t)j + 1]};
+            float vij[2] = {v[2 * (size_t)i] - v[2 * (size_t)j], v[2 * (size_t)i + 1] - v[2 * (size_t)j + 1]};
+            float gw[2];
+            cubic_kernel_derivative(c, r, gw);
+            double gn = sqrt((double)gw[0] * gw[0] + (double)gw[1] * gw[1]);
+            double rn = vnorm(r, 2);
+            snp += fabs(c->g1_visc_c * ((double)c->g1_mass / density_pre[j]) * vdot(vij, r, 2) /
+                        (rn * rn + c->eps_h2)) * gn;
+            if (material[j] == MAT_FLUID)
+                sp += fabs(c->g1_press_c * ((double)pressure[i] / ((double)density[i] * density[i]) +
+                                            (double)pressure[j] / ((double)density[j] * density[j]))) * gn;
+        }
+        mag_np[i] = (float)snp;
+        mag_p[i] = (float)sp;
+    }
+}
+
 /* One full gen-1 step (sph_base.py:168-172).  neighbors/neighbors_num are caller
  * scratch ([n][max_neighbors], [n]) and hold the reference's neighbour table on return. */
 int ora_step_gen1(const ora_config *c, int n, float *x, float *v, float *density,

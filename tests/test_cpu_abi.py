@@ -26,7 +26,8 @@ def test_library_exports_every_declared_symbol():
     for name in names:
         assert hasattr(lib, name), f"{name} declared in tisph.h but not exported"
     assert sorted(_capi.SYMBOLS) == names, "ctypes binding and header disagree"
-    assert lib.tisph_abi_version() == 1
+    header = open(os.path.join(ROOT, "include", "tisph.h")).read()
+    assert lib.tisph_abi_version() == _capi.ABI_VERSION == int(re.search(r"#define TISPH_ABI_VERSION (\d+)", header).group(1))
 
 
 def test_config_struct_matches_header_layout():

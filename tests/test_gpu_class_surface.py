@@ -1,0 +1,169 @@
+"""The drop-in classes driven kernel by kernel, exactly as tests/golden/make_golden.py:run_gen2 drives
+the reference's ParticleSystemV4 / WCSPHV2 (update_gird_id, prefix_sum_executor.run, resort,
+compute_volume_of_boundary_particle, compute_densities, compute_non_pressure_force,
+compute_pressure_force, advert, enforce_boundary), and every snapshot compared with what the
+reference's own sources recorded in tests/golden/*.npz.  Plus the extension points of the classes:
+subclass hooks, assignable solver attributes, ps.update() + solver.step().
+"""
+import copy
+import json
+import os
+
+import numpy as np
+import pytest
+
+from core.partice_system.partice_systemv4 import ParticleSystemV4
+from core.sph.wcsphv2 import WCSPHV2
+from ti_sph_b200 import _capi as K
+from util import RTOL, accel_err, golden_gen2_force_reference, rel_err, small_scene
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def build(case, z, tmp_path):
+    scene = copy.deepcopy(case["scene"])
+    for k, rb in enumerate(scene["rigidBodies"]):
+        path = os.path.join(tmp_path, f"rigid{k}.npy")
+        np.save(path, z["points." + rb["geometryFile"]])
+        rb["geometryFile"] = path
+    ps = ParticleSystemV4(scene)
+    return ps, WCSPHV2(ps)
+
+
+@pytest.mark.parametrize("name", ["gen2_block", "gen2_walls", "gen2_two_blocks", "gen2_boundary"])
+def test_kernel_by_kernel_driver_matches_the_reference_vectors(name, tmp_path):
+    z = np.load(os.path.join(GOLD, name + ".npz"))
+    case = json.loads(str(z["case_json"]))
+    ps, solver = build(case, z, str(tmp_path))
+    n = int(ps.particle_num[None])
+    assert n == int(z["n"]) == ps.particle_max_num
+    ps.engine.set_param(K.P_DIAGNOSTICS, 1)          # ps.paritcle_index_temp is a diagnostic here
+
+    def same(tag, *names, exact=True, floor=0.0):
+        for nm in names:
+            got = (solver.d_velocity if nm == "d_velocity" else getattr(ps, nm)).to_numpy()
+            want = z[f"{tag}.{nm}"]
+            if exact:
+                assert np.array_equal(got, want), f"{tag}.{nm}"
+            else:
+                assert rel_err(got, want, floor=floor) < RTOL, f"{tag}.{nm}"
+
+    same("init", "x", "v", "density", "pressure", "material", "color", "mass", "volume")
+    for s in range(1):        # (the second golden step starts from the reference's f32 trajectory: test_gpu_golden.py)
+        t = f"s{s}"
+        # ---- SPHBaseV2.step(), sph_basev2.py:210-214, call by call
+        ps.update_gird_id()
+        assert np.array_equal(ps.grid_particles_num.to_numpy(), z[f"{t}.counts"])
+        assert np.array_equal(ps.grid_ids.to_numpy(), z[f"{t}.sorted.grid_ids"][z[f"{t}.sorted.paritcle_index_temp"]])
+        ps.prefix_sum_executor.run(ps.grid_particles_num)
+        ps.resort()
+        same(t + ".sorted", "grid_ids", "grid_particles_num", "paritcle_index_temp", "x", "v", "density", "pressure",
+             "material", "color", "mass", "volume")
+        solver.compute_volume_of_boundary_particle()
+        same(t + ".volume", "volume", exact=False)
+        solver.compute_densities()
+        same(t + ".density", "density", exact=False)
+        assert np.array_equal(ps.pressure.to_numpy(), z[f"{t}.sorted.pressure"])     # not written yet
+        solver.compute_non_pressure_force()
+        fl = z[f"{t}.sorted.material"] == 1
+        ref = golden_gen2_force_reference(case, z, s)       # golden arrays + the magnitude sums that scale 1e-5
+        assert accel_err(solver.d_velocity.to_numpy(), ref["a_nonpressure"], ref["mag_nonpressure"]) < RTOL
+        assert np.array_equal(ps.x.to_numpy(), z[f"{t}.sorted.x"])                   # not advected yet
+        solver.compute_pressure_force()
+        same(t + ".pressure", "density", exact=False)
+        p, p_ref = ps.pressure.to_numpy().astype(np.float64), z[f"{t}.pressure.pressure"].astype(np.float64)
+        x7 = (z[f"{t}.pressure.density"].astype(np.float64) / 1000.0) ** 7
+        assert np.all(np.abs(p - p_ref)[fl] <= (RTOL * np.abs(p_ref) + 50 * 8 * np.finfo(np.float32).eps * x7)[fl])
+        mag = ref["mag_nonpressure"].astype(np.float64) + ref["mag_pressure"]
+        assert accel_err(solver.d_velocity.to_numpy(), ref["d_velocity"], mag, ref["mag_pressure_floor"]) < RTOL
+        scale = float((mag + ref["mag_pressure_floor"] / RTOL).max())
+        assert np.array_equal(ps.x.to_numpy(), z[f"{t}.sorted.x"])
+        solver.advert()
+        same(t + ".advert", "x", exact=False, floor=0.04)       # advected, walls not applied
+        assert rel_err(ps.v.to_numpy(), z[f"{t}.advert.v"], floor=1.0) < RTOL + 2e-4 * scale * RTOL
+        solver.enforce_boundary()
+        same(t + ".end", "x", exact=False, floor=0.04)
+        assert rel_err(ps.v.to_numpy(), z[f"{t}.end.v"], floor=1.0) < RTOL + 2e-4 * scale * RTOL
+        same(t + ".end", "material", "color", "mass")
+        d = ps.dump()
+        assert np.array_equal(d["material"], z[f"{t}.dump.material"]) and np.array_equal(d["color"], z[f"{t}.dump.color"])
+        assert rel_err(d["position"], z[f"{t}.dump.position"], floor=0.04) < RTOL
+        np_x = np.zeros((n, 3), np.float32)
+        ps.copy_to_numpy_nd(np_x, ps.x)
+        np_m = np.zeros(n, np.int32)
+        ps.copy_to_numpy(np_m, ps.material)
+        assert np.array_equal(np_x, d["position"]) and np.array_equal(np_m, d["material"])
+    if name == "gen2_walls":     # the walls moved something in this case, so advert() and the end state differ
+        assert not np.array_equal(z["s0.advert.x"], z["s0.end.x"])
+    # the unmodified step() on a second system reaches the same state
+    ps2, solver2 = build(case, z, str(tmp_path))
+    solver2.step()
+    assert np.array_equal(ps2.x.to_numpy(), ps.x.to_numpy()) and np.array_equal(ps2.v.to_numpy(), ps.v.to_numpy())
+    ps.engine.close(); ps2.engine.close()
+
+
+def test_subclass_hooks_are_called_in_the_reference_order():
+    calls = []
+
+    class Probe(WCSPHV2):
+        def substep(self):
+            calls.append("substep")
+            super().substep()
+
+        def enforce_boundary(self):
+            calls.append("enforce_boundary")
+            super().enforce_boundary()
+
+    scene = small_scene(end=(0.4, 0.2, 0.8))
+    ps, ps_ref = ParticleSystemV4(copy.deepcopy(scene)), ParticleSystemV4(copy.deepcopy(scene))
+    probe, stock = Probe(ps), WCSPHV2(ps_ref)
+    for _ in range(2):
+        probe.step()
+        stock.step()
+    assert calls == ["substep", "enforce_boundary"] * 2
+    assert np.array_equal(ps.x.to_numpy(), ps_ref.x.to_numpy()) and np.array_equal(ps.v.to_numpy(), ps_ref.v.to_numpy())
+    # ps.update() by the script, then solver.step(): the step continues from the sorted state
+    ps.update()
+    probe.step()
+    ps_ref.update()
+    stock.step()
+    assert np.array_equal(ps.x.to_numpy(), ps_ref.x.to_numpy())
+    ps.engine.close(); ps_ref.engine.close()
+
+
+def test_solver_attributes_are_assignable_after_construction():
+    from oracle.oracle import Gen2Oracle
+    scene = small_scene(end=(0.4, 0.2, 0.8))
+    scene["fluidBlocks"][0]["density"] = 4000.0          # mass W(0) > rho0: the Tait pressure works
+    ps = ParticleSystemV4(copy.deepcopy(scene))
+    solver = WCSPHV2(ps)
+    solver.stiffness, solver.exponent, solver.viscosity = 80.0, 5.0, 0.02
+    solver.g[1] = -3.0
+    solver.dt[None] = 1e-4
+    assert (solver.stiffness, solver.exponent) == (80.0, 5.0) and solver.viscosity == pytest.approx(0.02)
+    ora = Gen2Oracle(scene)
+    ora.cfg.stiffness, ora.cfg.exponent, ora.cfg.dt = 80.0, 5.0, 1e-4
+    ora.cfg.visc_fluid_c = 2 * 0.02 * ora.support_length * scene["configuration"]["c_s"]
+    ora.cfg.g[1] = -3.0
+    solver.step()
+    t = ora.step(trace=True)
+    assert np.array_equal(ps.engine.download(K.F_ORIG_ID), t["orig"])
+    assert float(np.abs(t["pressure"]).max()) > 0
+    assert rel_err(ps.pressure.to_numpy(), t["pressure"], floor=1.0) < RTOL
+    assert rel_err(ps.x.to_numpy(), t["x"], floor=0.04) < RTOL
+    assert rel_err(ps.v.to_numpy(), t["v"], floor=1.0) < RTOL
+    ps.engine.close()
+
+
+def test_zero_copy_view_right_after_step_needs_no_manual_sync():
+    """ps.x handed to torch straight after step(): the view orders itself after the engine's stream"""
+    import torch
+    ps = ParticleSystemV4(small_scene(end=(0.5, 0.3, 0.9)))
+    solver = WCSPHV2(ps)
+    for _ in range(3):
+        solver.step()
+        x_dev = ps.x.to_torch()                    # no engine.sync() in between
+        x_host = ps.x.to_numpy()
+        assert np.array_equal(x_dev.cpu().numpy(), x_host)
+    ps.engine.close()

@@ -14,7 +14,7 @@ import pytest
 from ti_sph_b200 import _capi as K
 from ti_sph_b200 import scene as sc
 from ti_sph_b200.engine import Engine
-from util import RTOL, rel_err, vec_rel_err
+from util import RTOL, check_force_stage, golden_gen2_force_reference, rel_err
 
 pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
@@ -56,12 +56,8 @@ def test_gen2_step_matches_the_reference_vectors(name, variant):
             assert np.all(np.abs(p - p_ref)[fl] <= (RTOL * np.abs(p_ref) + 50 * 8 * np.finfo(np.float32).eps * x7)[fl])
             assert rel_err(eng.download(K.F_VOLUME), g("volume.volume")) < RTOL
             eng.stage(K.STAGE_FORCE_ADVECT)
-            a_np_ref, a_ref = g("nonpressure.d_velocity"), g("pressure.d_velocity")
-            assert vec_rel_err(eng.download(K.F_A_NONPRESSURE)[fl], a_np_ref[fl], floor=50.0) < RTOL
-            pfl = max(50.0, float(np.abs(a_ref).max()))
-            assert vec_rel_err(eng.download(K.F_D_VELOCITY)[fl], a_ref[fl], floor=pfl) < RTOL
-            assert rel_err(eng.download(K.F_X), g("end.x"), floor=0.04) < RTOL
-            assert vec_rel_err(eng.download(K.F_V), g("end.v"), floor=1.0) < RTOL + 2e-4 * pfl * RTOL
+            t = golden_gen2_force_reference(case, z, s)
+            check_force_stage(eng, t)
             assert np.array_equal(eng.download(K.F_MATERIAL), g("end.material"))
         eng.sync()
         eng.close()

@@ -35,12 +35,17 @@ class Config(C.Structure):
 # enum tisph_field
 F_X, F_V, F_MASS, F_VOLUME, F_DENSITY, F_PRESSURE, F_MATERIAL, F_COLOR, F_GRID_IDS, \
     F_GRID_PARTICLES_NUM, F_D_VELOCITY, F_DENSITY_SUM, F_DENSITY_RAW, F_NEIGHBOR_COUNT, \
-    F_ORIG_ID, F_A_NONPRESSURE, F_A_PRESSURE, F_CELL_COUNT, F_NEIGHBORS = range(19)
+    F_ORIG_ID, F_A_NONPRESSURE, F_A_PRESSURE, F_CELL_COUNT, F_NEIGHBORS, F_X_IN, F_V_IN, \
+    F_PRESSURE_STORED, F_PARTICLE_INDEX = range(23)
 # enum tisph_stage
-STAGE_UPDATE, STAGE_DENSITY, STAGE_FORCE_ADVECT = range(3)
+STAGE_UPDATE, STAGE_DENSITY, STAGE_FORCE_ADVECT, STAGE_UPDATE_BIN, STAGE_UPDATE_SCAN, STAGE_UPDATE_SORT, \
+    STAGE_WALLS = range(7)
 # enum tisph_param
 P_DT, P_DENSITY_MODE, P_VOLUME_MODE, P_DIAGNOSTICS, P_KERNEL_VARIANT, P_ID_BASE, P_HAS_BOUNDARY, \
-    P_STAT_ITEMS, P_STAT_FALLBACK_DENSITY, P_STAT_FALLBACK_FORCE, P_CFL, P_STAT_CHECK_FAILURES = range(12)
+    P_STAT_ITEMS, P_STAT_FALLBACK_DENSITY, P_STAT_FALLBACK_FORCE, P_CFL, P_STAT_CHECK_FAILURES, \
+    P_SPLIT_WALLS, P_PHASE, P_STIFFNESS, P_EXPONENT, P_VISCOSITY, P_DENSITY0, P_GRAVITY_X, P_GRAVITY_Y, \
+    P_GRAVITY_Z, P_MAX_SPEED = range(22)
+ABI_VERSION = 2
 
 ERR_NO_DEVICE = -5
 
@@ -90,6 +95,8 @@ def load():
     if _lib is not None:
         return _lib
     path = library_path()
+    if os.path.exists(path) and not _build.is_fresh() and _build.have_nvcc():
+        _build.build()                       # stale against csrc/ or include/: rebuild rather than run old kernels
     if not os.path.exists(path):
         raise ImportError(
             f"{path} is missing: build it with `python -m ti_sph_b200.build` (needs nvcc). "
@@ -99,8 +106,9 @@ def load():
         fn = getattr(lib, name)          # AttributeError if the export is missing
         fn.restype = res
         fn.argtypes = args
-    if lib.tisph_abi_version() != 1:
-        raise ImportError("libtisph.so ABI version mismatch; rebuild it")
+    if lib.tisph_abi_version() != ABI_VERSION:
+        raise ImportError(f"{path} has ABI version {lib.tisph_abi_version()}, this package binds {ABI_VERSION}: "
+                          "rebuild it with `python -m ti_sph_b200.build --force`")
     _lib = lib
     return lib
 

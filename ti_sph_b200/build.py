@@ -38,6 +38,10 @@ def is_fresh():
         return False
 
 
+def have_nvcc():
+    return bool(shutil.which("nvcc")) or os.path.exists("/usr/local/cuda/bin/nvcc")
+
+
 def build(force=False, verbose=False):
     """Compile the library if it is missing or stale. Returns its path."""
     if not force and is_fresh():

@@ -56,6 +56,9 @@ struct tisph_ctx {
     float4 *P[2] = {nullptr, nullptr}, *V[2] = {nullptr, nullptr}, *Q[2] = {nullptr, nullptr};
     int cur = 0;         // which copy holds the authoritative particle records
     int phase = 0;       // 0: between steps, 1: after UPDATE, 2: after DENSITY
+    int uphase = 0;      // inside UPDATE: 1 after UPDATE_BIN, 2 after UPDATE_SCAN
+    bool walls_pending = false;     // a split force stage ran: TISPH_STAGE_WALLS is due
+    int* new_index = nullptr;       // paritcle_index_temp (diagnostics only)
     bool have_sorted = false;
     float4 *D = nullptr, *dvel = nullptr, *a_np = nullptr, *a_p = nullptr;
     float* S = nullptr;
@@ -118,6 +121,17 @@ static float d2_cutoff(float h) {
     return t;
 }
 
+static void fill_params(tisph_ctx* c);
+// the solver attributes changed (tisph_set_param): refresh the kernels' copy, keep the run-time state
+static void fill_physics(tisph_ctx* c) {
+    SimParams keep = c->sp;
+    fill_params(c);
+    c->sp.n = keep.n; c->sp.dt = keep.dt; c->sp.walls = keep.walls;
+    c->sp.own_key_lo = keep.own_key_lo; c->sp.own_key_hi = keep.own_key_hi;
+    c->sp.walk_key_lo = keep.walk_key_lo; c->sp.walk_key_hi = keep.walk_key_hi;
+    c->sp.ghost_walk = keep.ghost_walk;
+}
+
 static void fill_params(tisph_ctx* c) {
     const tisph_config& g = c->cfg;
     SimParams& s = c->sp;
@@ -141,6 +155,7 @@ static void fill_params(tisph_ctx* c) {
     float e = g.exponent;
     s.int_exponent = (e >= 1.0f && e <= 64.0f && e == floorf(e)) ? (int)e : 0;
     s.one = 1.0f;
+    s.walls = 1;
     s.own_key_lo = 0; s.own_key_hi = 0x7fffffff;
     s.walk_key_lo = 0; s.walk_key_hi = 0x7fffffff;
     s.ghost_walk = 1;
@@ -205,39 +220,51 @@ static int run_update_gen1(tisph_ctx* c) {
     return TISPH_OK;
 }
 
-static int run_update(tisph_ctx* c) {
-    if (c->phase != 0) return fail(TISPH_ERR_INVALID, "UPDATE issued out of order (phase %d)", c->phase);
-    if (c->cfg.generation == 1) return run_update_gen1(c);
+// ps.update() = update_gird_id + PrefixSumExecutor.run + resort (partice_systemv4.py:251-256), as the
+// three sub-stages of the ABI or in one go
+static int run_update_bin(tisph_ctx* c) {
+    if (c->phase != 0 || c->uphase != 0)
+        return fail(TISPH_ERR_INVALID, "UPDATE issued out of order (phase %d.%d)", c->phase, c->uphase);
+    if (c->walls_pending) return fail(TISPH_ERR_INVALID, "TISPH_STAGE_WALLS is due (the last force stage ran split)");
     cudaStream_t st = c->stream;
     c->sp.n = c->n;
-    int a = c->cur, b = c->cur ^ 1;
-    if (c->n == 0) {
-        if (!c->sharded) return fail(TISPH_ERR_INVALID, "no particles");
-        // an empty slab (nothing owned, nothing received) still takes part in every exchange
-        CU(cudaMemsetAsync(c->cell_count, 0, sizeof(int) * (size_t)c->ncell, st));
-        CU(cudaMemsetAsync(c->cell_end, 0, sizeof(int) * (size_t)c->ncell, st));
-        CU(cudaMemsetAsync(c->ctr, 0, sizeof(StepCounters), st));
-        CU(cudaMemsetAsync(c->range_dev, 0, 2 * sizeof(int), st));
-        c->range_valid = false;
-        c->in_off = 0; c->appended = false;
-        c->cur = b; c->phase = 1; c->have_sorted = true;
-        return TISPH_OK;
-    }
-    int nb_cells = nblocks(c->ncell, SCAN_TILE);
     CU(cudaMemsetAsync(c->cell_count, 0, sizeof(int) * (size_t)c->ncell, st));
     CU(cudaMemsetAsync(c->ctr, 0, sizeof(StepCounters), st));
-    const float4 *Pin = c->P[a] + c->in_off, *Vin = c->V[a] + c->in_off, *Qin = c->Q[a] + c->in_off;
-    k_bin<<<nblocks(c->n, 256), 256, 0, st>>>(c->sp, Pin, c->keys, c->arrival, c->cell_count, c->err_dev);
+    k_bin<<<nblocks(c->n, 256), 256, 0, st>>>(c->sp, c->P[c->cur] + c->in_off, c->keys, c->arrival, c->cell_count, c->err_dev);
+    c->launches += 1;
+    CU(cudaGetLastError());
+    c->uphase = 1;
+    return TISPH_OK;
+}
+
+static int run_update_scan(tisph_ctx* c) {
+    if (c->phase != 0 || c->uphase != 1)
+        return fail(TISPH_ERR_INVALID, "UPDATE_SCAN issued out of order (phase %d.%d)", c->phase, c->uphase);
+    cudaStream_t st = c->stream;
+    int nb_cells = nblocks(c->ncell, SCAN_TILE);
     k_scan_reduce<<<nb_cells, SCAN_THREADS, 0, st>>>(c->cell_count, c->ncell, c->block_sums);
     k_scan_spine<<<1, 1024, 0, st>>>(c->block_sums, nb_cells);
     k_scan_apply<<<nb_cells, SCAN_THREADS, 0, st>>>(c->cell_count, c->ncell, c->block_sums, c->cell_end);
+    c->launches += 3;
+    CU(cudaGetLastError());
+    c->uphase = 2;
+    return TISPH_OK;
+}
+
+static int run_update_sort(tisph_ctx* c) {
+    if (c->phase != 0 || c->uphase != 2)
+        return fail(TISPH_ERR_INVALID, "UPDATE_SORT issued out of order (phase %d.%d)", c->phase, c->uphase);
+    cudaStream_t st = c->stream;
+    int a = c->cur, b = c->cur ^ 1;
+    const float4 *Pin = c->P[a] + c->in_off, *Vin = c->V[a] + c->in_off, *Qin = c->Q[a] + c->in_off;
     k_place<<<nblocks(c->n, 256), 256, 0, st>>>(c->n, c->keys, c->arrival, c->cell_end, c->ids,
                                                 c->sharded ? Qin : nullptr, c->rank_key);
     k_reorder<<<nblocks(c->n, 256), 256, 0, st>>>(c->n, c->keys, c->ids, c->rank_key, c->cell_end, Pin, Vin,
-                                                  Qin, c->P[b], c->V[b], c->Q[b], c->keys_sorted);
+                                                  Qin, c->P[b], c->V[b], c->Q[b], c->keys_sorted,
+                                                  c->diagnostics ? c->new_index : nullptr);
     k_items<<<nblocks(c->ncell, 256), 256, 0, st>>>(c->sp, c->sp.walk_key_lo, c->sp.walk_key_hi, c->cell_end,
                                                     c->items, c->ctr);
-    c->launches += 7;
+    c->launches += 3;
     if (c->sharded) {
         k_owned_range<<<1, 1, 0, st>>>(c->cell_end, c->ncell, c->sp.own_key_lo, c->sp.own_key_hi, c->range_dev);
         c->launches += 1;
@@ -248,7 +275,45 @@ static int run_update(tisph_ctx* c) {
     c->appended = false;
     c->cur = b;
     c->phase = 1;
+    c->uphase = 0;
     c->have_sorted = true;
+    return TISPH_OK;
+}
+
+static int run_update(tisph_ctx* c) {
+    if (c->phase != 0 || c->uphase != 0)
+        return fail(TISPH_ERR_INVALID, "UPDATE issued out of order (phase %d.%d)", c->phase, c->uphase);
+    if (c->cfg.generation == 1) return run_update_gen1(c);
+    if (c->n == 0) {
+        if (!c->sharded) return fail(TISPH_ERR_INVALID, "no particles");
+        // an empty slab (nothing owned, nothing received) still takes part in every exchange
+        cudaStream_t st = c->stream;
+        CU(cudaMemsetAsync(c->cell_count, 0, sizeof(int) * (size_t)c->ncell, st));
+        CU(cudaMemsetAsync(c->cell_end, 0, sizeof(int) * (size_t)c->ncell, st));
+        CU(cudaMemsetAsync(c->ctr, 0, sizeof(StepCounters), st));
+        CU(cudaMemsetAsync(c->range_dev, 0, 2 * sizeof(int), st));
+        c->range_valid = false;
+        c->in_off = 0; c->appended = false;
+        c->cur ^= 1; c->phase = 1; c->have_sorted = true;
+        return TISPH_OK;
+    }
+    int rc;
+    if ((rc = run_update_bin(c))) return rc;
+    if ((rc = run_update_scan(c))) return rc;
+    return run_update_sort(c);
+}
+
+static int run_walls(tisph_ctx* c) {
+    if (c->phase != 0 || !c->walls_pending) return fail(TISPH_ERR_INVALID, "WALLS follows a split FORCE_ADVECT stage");
+    int rc = ensure_range(c);
+    if (rc) return rc;
+    int n = c->o_hi - c->o_lo;
+    if (n > 0)
+        k_walls<<<nblocks(n, 256), 256, 0, c->stream>>>(c->sp, n, c->P[c->cur] + c->o_lo, c->V[c->cur] + c->o_lo,
+                                                        c->Q[c->cur] + c->o_lo);
+    c->launches += 1;
+    CU(cudaGetLastError());
+    c->walls_pending = false;
     return TISPH_OK;
 }
 
@@ -293,6 +358,7 @@ static int run_force(tisph_ctx* c) {
         c->phase = 0;
         return TISPH_OK;
     }
+    c->walls_pending = c->sp.walls == 0;
     auto kf = c->has_boundary ? k_force_list<true> : k_force_list<false>;
     kf<<<c->grid_fl, NB_THREADS, FL_SMEM, st>>>(
         c->sp, c->cell_end, c->items, c->ctr, c->P[b], c->V[b], c->Q[b], c->D, c->P[a], c->V[a], c->Q[a],
@@ -422,7 +488,7 @@ int tisph_destroy(tisph_ctx* c) {
     cudaSetDevice(c->cfg.device);
     if (c->own_stream) cudaStreamSynchronize(c->own_stream);
     for (int k = 0; k < 2; ++k) { cudaFree(c->P[k]); cudaFree(c->V[k]); cudaFree(c->Q[k]); }
-    cudaFree(c->D); cudaFree(c->dvel); cudaFree(c->a_np); cudaFree(c->a_p); cudaFree(c->S);
+    cudaFree(c->D); cudaFree(c->dvel); cudaFree(c->a_np); cudaFree(c->a_p); cudaFree(c->new_index); cudaFree(c->S);
     cudaFree(c->ncount); cudaFree(c->keys); cudaFree(c->arrival); cudaFree(c->ids);
     cudaFree(c->keys_sorted); cudaFree(c->cell_count); cudaFree(c->cell_end);
     cudaFree(c->snapP); cudaFree(c->snapV); cudaFree(c->snapQ);
@@ -498,7 +564,7 @@ int tisph_add_particles(tisph_ctx* c, int32_t n, const float* pos, const float* 
 int tisph_reset(tisph_ctx* c) {
     CHECK_CTX(c);
     CU(cudaStreamSynchronize(c->stream));
-    c->n = 0; c->sp.n = 0; c->phase = 0; c->have_sorted = false; c->id_base = 0;
+    c->n = 0; c->sp.n = 0; c->phase = 0; c->uphase = 0; c->walls_pending = false; c->have_sorted = false; c->id_base = 0;
     CU(cudaMemsetAsync(c->err_dev, 0, 16, c->stream));
     return set_owned_all(c);
 }
@@ -547,6 +613,24 @@ int tisph_state_restore(tisph_ctx* c) {
     return set_owned_all(c);
 }
 
+// max |v|^2 over the owned fluid particles (synchronises)
+static int max_speed2(tisph_ctx* c, float* v2) {
+    int rc = ensure_range(c);
+    if (rc) return rc;
+    unsigned int bits = 0u;
+    unsigned int* d = (unsigned int*)(c->err_dev + 2);
+    int n_own = c->o_hi - c->o_lo;
+    CU(cudaMemsetAsync(d, 0, 4, c->stream));
+    if (n_own > 0)
+        k_vmax<<<nblocks(n_own, 256) < 1184 ? nblocks(n_own, 256) : 1184, 256, 0, c->stream>>>(
+            n_own, c->V[c->cur] + c->o_lo, c->Q[c->cur] + c->o_lo, d);
+    c->launches += 1;
+    CU(cudaMemcpyAsync(&bits, d, 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    memcpy(v2, &bits, 4);
+    return TISPH_OK;
+}
+
 static int make_events(tisph_ctx* c) {
     if (c->ev_made) return TISPH_OK;
     for (int s = 0; s < MAX_TIMED_STEPS; ++s)
@@ -557,26 +641,16 @@ static int make_events(tisph_ctx* c) {
 
 int tisph_step(tisph_ctx* c, int32_t nsteps) {
     CHECK_CTX(c);
-    if (c->phase != 0) return fail(TISPH_ERR_INVALID, "step issued in the middle of a staged step");
+    if (c->phase != 0 || c->uphase != 0 || c->walls_pending)
+        return fail(TISPH_ERR_INVALID, "step issued in the middle of a staged step");
     if (c->sharded && nsteps > 1)
         return fail(TISPH_ERR_INVALID, "a sharded context needs a halo exchange before every step");
     for (int s = 0; s < nsteps; ++s) {
         bool t = c->timing && c->timed < MAX_TIMED_STEPS;
         int rc;
         if (c->cfl > 0.f && !c->appended) {     // optional CFL step (extension): one small reduction + one sync per step
-            if ((rc = ensure_range(c))) return rc;
-            unsigned int bits = 0u;
-            unsigned int* d = (unsigned int*)(c->err_dev + 2);
-            int n_own = c->o_hi - c->o_lo;
-            CU(cudaMemsetAsync(d, 0, 4, c->stream));
-            if (n_own > 0)
-                k_vmax<<<nblocks(n_own, 256) < 1184 ? nblocks(n_own, 256) : 1184, 256, 0, c->stream>>>(
-                    n_own, c->V[c->cur] + c->o_lo, c->Q[c->cur] + c->o_lo, d);
-            c->launches += 1;
-            CU(cudaMemcpyAsync(&bits, d, 4, cudaMemcpyDeviceToHost, c->stream));
-            CU(cudaStreamSynchronize(c->stream));
-            float v2;
-            memcpy(&v2, &bits, 4);
+            float v2 = 0.f;
+            if ((rc = max_speed2(c, &v2))) return rc;
             float dt = c->cfl * c->cfg.support / (c->cfg.c_s + sqrtf(v2));
             c->sp.dt = dt < c->cfg.dt ? dt : c->cfg.dt;
         }
@@ -597,6 +671,14 @@ int tisph_stage_run(tisph_ctx* c, int32_t stage) {
         case TISPH_STAGE_UPDATE: return run_update(c);
         case TISPH_STAGE_DENSITY: return run_density(c);
         case TISPH_STAGE_FORCE_ADVECT: return run_force(c);
+        case TISPH_STAGE_UPDATE_BIN:
+        case TISPH_STAGE_UPDATE_SCAN:
+        case TISPH_STAGE_UPDATE_SORT:
+            if (c->cfg.generation != 2 || c->n == 0)
+                return fail(TISPH_ERR_INVALID, "the update sub-stages are those of ParticleSystemV4 with particles");
+            return stage == TISPH_STAGE_UPDATE_BIN ? run_update_bin(c)
+                   : stage == TISPH_STAGE_UPDATE_SCAN ? run_update_scan(c) : run_update_sort(c);
+        case TISPH_STAGE_WALLS: return run_walls(c);
     }
     return fail(TISPH_ERR_INVALID, "unknown stage %d", stage);
 }
@@ -655,9 +737,16 @@ int tisph_download(tisph_ctx* c, int32_t field, void* dst, size_t bytes) {
         case TISPH_F_NEIGHBORS:
             if (c->cfg.generation != 1) return fail(TISPH_ERR_INVALID, "gen-2 keeps no explicit neighbour table");
             direct = c->nbr; count = (size_t)n * G1_MAX_NEIGHBORS; break;
-        case TISPH_F_GRID_IDS: direct = c->keys_sorted; break;
+        case TISPH_F_GRID_IDS: direct = c->uphase ? c->keys : c->keys_sorted; break;   // unsorted between bin and sort
         case TISPH_F_GRID_PARTICLES_NUM:      // gen-2: inclusive scan; gen-1: per-cell counts (partice_system.py:131)
-            direct = c->cfg.generation == 1 ? c->cell_count : c->cell_end; count = (size_t)c->ncell; break;
+            direct = (c->cfg.generation == 1 || c->uphase == 1) ? c->cell_count : c->cell_end;   // histogram until the scan ran
+            count = (size_t)c->ncell; break;
+        case TISPH_F_X_IN: src = c->P[c->phase ? cur : cur ^ 1]; comp0 = 0; ncomp = dim; break;
+        case TISPH_F_V_IN: src = c->V[c->phase ? cur : cur ^ 1]; comp0 = 0; ncomp = dim; break;
+        case TISPH_F_PRESSURE_STORED: src = c->Q[c->phase ? cur : cur ^ 1]; comp0 = 1; break;
+        case TISPH_F_PARTICLE_INDEX:
+            if (!c->new_index || !c->diagnostics) return fail(TISPH_ERR_INVALID, "enable TISPH_P_DIAGNOSTICS before the step");
+            direct = c->new_index; break;
         case TISPH_F_CELL_COUNT: direct = c->cell_count; count = (size_t)c->ncell; break;
         case TISPH_F_COLOR:
             if (c->sharded) return fail(TISPH_ERR_INVALID, "colour is kept by the host side of a sharded run");
@@ -721,7 +810,27 @@ int tisph_set_param(tisph_ctx* c, int32_t param, double value) {
     CHECK_CTX(c);
     switch (param) {
         case TISPH_P_DT: c->cfg.dt = (float)value; c->sp.dt = (float)value; return TISPH_OK;
-        case TISPH_P_CFL: c->cfl = (float)value; if (c->cfl <= 0.f) c->sp.dt = c->cfg.dt; return TISPH_OK;
+        case TISPH_P_CFL:
+            if (c->sharded && value > 0.0)
+                return fail(TISPH_ERR_INVALID, "TISPH_P_CFL on a sharded context: the ranks must agree on dt "
+                                               "(max-reduce TISPH_P_MAX_SPEED and set TISPH_P_DT)");
+            c->cfl = (float)value; if (c->cfl <= 0.f) c->sp.dt = c->cfg.dt; return TISPH_OK;
+        case TISPH_P_SPLIT_WALLS:
+            if (c->phase == 0 && c->walls_pending) return fail(TISPH_ERR_INVALID, "TISPH_STAGE_WALLS is due");
+            c->sp.walls = value != 0.0 ? 0 : 1; return TISPH_OK;
+        case TISPH_P_STIFFNESS: c->cfg.stiffness = c->sp.stiffness = (float)value; return TISPH_OK;
+        case TISPH_P_EXPONENT: c->cfg.exponent = (float)value; fill_physics(c); return TISPH_OK;
+        case TISPH_P_VISCOSITY:      // wcsphv2.py:69 (2 nu h c_s) ; sph_base.py:81 (2 (dim+2) nu)
+            c->cfg.visc_fluid_c = (float)(2.0 * value * c->cfg.support * c->cfg.c_s);
+            c->cfg.g1_visc_c = (float)(2.0 * (c->cfg.dim + 2) * value);
+            fill_physics(c); return TISPH_OK;
+        case TISPH_P_DENSITY0:       // sph_basev2.py:13 ; gen-1: sph_base.py:16,68
+            c->cfg.rho0 = (float)value;
+            c->cfg.g1_mass = (float)(c->cfg.m_V0 * value);
+            c->cfg.g1_press_c = (float)(-value * c->cfg.m_V0);
+            fill_physics(c); return TISPH_OK;
+        case TISPH_P_GRAVITY_X: case TISPH_P_GRAVITY_Y: case TISPH_P_GRAVITY_Z:
+            c->cfg.gravity[param - TISPH_P_GRAVITY_X] = (float)value; fill_physics(c); return TISPH_OK;
         case TISPH_P_DENSITY_MODE: c->cfg.density_mode = (int)value; c->sp.density_mode = (int)value; return TISPH_OK;
         case TISPH_P_VOLUME_MODE: c->cfg.volume_mode = (int)value; c->sp.volume_mode = (int)value; return TISPH_OK;
         case TISPH_P_DIAGNOSTICS:
@@ -729,6 +838,8 @@ int tisph_set_param(tisph_ctx* c, int32_t param, double value) {
             if (c->diagnostics && !c->a_np) {
                 CU(dalloc(&c->a_np, (size_t)c->cap));
                 CU(dalloc(&c->a_p, (size_t)c->cap));
+                CU(dalloc(&c->new_index, (size_t)c->cap));
+                CU(cudaMemsetAsync(c->new_index, 0, (size_t)c->cap * 4, c->stream));
                 CU(cudaMemsetAsync(c->a_np, 0, (size_t)c->cap * 16, c->stream));
                 CU(cudaMemsetAsync(c->a_p, 0, (size_t)c->cap * 16, c->stream));
             }
@@ -755,6 +866,25 @@ int tisph_get_param(tisph_ctx* c, int32_t param, double* value) {
 #else
             *value = -1.0;                                // checks are compiled out
 #endif
+            return TISPH_OK;
+        }
+        case TISPH_P_SPLIT_WALLS: *value = c->sp.walls ? 0 : 1; return TISPH_OK;
+        case TISPH_P_PHASE: *value = c->phase + 10 * c->uphase; return TISPH_OK;
+        case TISPH_P_STIFFNESS: *value = c->cfg.stiffness; return TISPH_OK;
+        case TISPH_P_EXPONENT: *value = c->cfg.exponent; return TISPH_OK;
+        case TISPH_P_VISCOSITY: *value = c->cfg.generation == 1 ? c->cfg.g1_visc_c / (2.0 * (c->cfg.dim + 2))
+                                                                : c->cfg.visc_fluid_c / (2.0 * c->cfg.support * c->cfg.c_s);
+            return TISPH_OK;
+        case TISPH_P_DENSITY0: *value = c->cfg.rho0; return TISPH_OK;
+        case TISPH_P_GRAVITY_X: case TISPH_P_GRAVITY_Y: case TISPH_P_GRAVITY_Z:
+            *value = c->cfg.gravity[param - TISPH_P_GRAVITY_X]; return TISPH_OK;
+        case TISPH_P_MAX_SPEED: {
+            CU(cudaSetDevice(c->cfg.device));
+            if (c->phase != 0 || c->appended) return fail(TISPH_ERR_INVALID, "max |v| is that of a completed step");
+            float v2 = 0.f;
+            int rc = max_speed2(c, &v2);
+            if (rc) return rc;
+            *value = sqrtf(v2);
             return TISPH_OK;
         }
         case TISPH_P_DENSITY_MODE: *value = c->cfg.density_mode; return TISPH_OK;

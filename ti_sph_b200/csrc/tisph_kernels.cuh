@@ -181,7 +181,7 @@ k_reorder(int n, const int* __restrict__ keys, const int* __restrict__ ids,
           const int* __restrict__ rank_key, const int* __restrict__ cell_end, const float4* __restrict__ Pin,
           const float4* __restrict__ Vin, const float4* __restrict__ Qin,
           float4* __restrict__ Pout, float4* __restrict__ Vout, float4* __restrict__ Qout,
-          int* __restrict__ keys_sorted) {
+          int* __restrict__ keys_sorted, int* __restrict__ new_index) {
     int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n) return;
     int id = ids[s];
@@ -195,6 +195,7 @@ k_reorder(int n, const int* __restrict__ keys, const int* __restrict__ ids,
     Vout[dst] = Vin[id];
     Qout[dst] = Qin[id];
     keys_sorted[dst] = key;
+    if (new_index) new_index[id] = dst;           // paritcle_index_temp (diagnostics)
 }
 
 // ---------------------------------------------------------------------------------------

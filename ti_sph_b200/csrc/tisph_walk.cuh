@@ -97,6 +97,35 @@ __device__ __forceinline__ void density_epilogue(const SimParams& sp, int i, flo
     ncount[i] = cnt;
 }
 
+// enforce_boundary_3D_v1 + simulate_collisions_v1 (sph_basev2.py:151-189): clamp to the padded box, reflect
+// the velocity about the accumulated wall normal; the wall tests use the pre-clamp position
+__device__ __forceinline__ void apply_walls(const SimParams& sp, float4& pout, float4& vout) {
+    const float px = pout.x, py = pout.y, pz = pout.z;
+    float cnx = 0.f, cny = 0.f, cnz = 0.f;
+    if (px > sp.wall_hi[0]) { cnx += 1.f; pout.x = sp.wall_hi[0]; }
+    if (px <= sp.pad)       { cnx -= 1.f; pout.x = sp.pad; }
+    if (py > sp.wall_hi[1]) { cny += 1.f; pout.y = sp.wall_hi[1]; }
+    if (py <= sp.pad)       { cny -= 1.f; pout.y = sp.pad; }
+    if (pz > sp.wall_hi[2]) { cnz += 1.f; pout.z = sp.wall_hi[2]; }
+    if (pz <= sp.pad)       { cnz -= 1.f; pout.z = sp.pad; }
+    float len = sqrtf(cnx * cnx + cny * cny + cnz * cnz);
+    if (len > 1e-6f) {
+        float ux = cnx / len, uy = cny / len, uz = cnz / len;
+        float sdot = 1.5f * (vout.x * ux + vout.y * uy + vout.z * uz);   // :151-156
+        vout.x -= sdot * ux; vout.y -= sdot * uy; vout.z -= sdot * uz;
+    }
+}
+
+// enforce_boundary() as a launch of its own (TISPH_STAGE_WALLS)
+__global__ void __launch_bounds__(256)
+k_walls(SimParams sp, int n, float4* __restrict__ P, float4* __restrict__ V, const float4* __restrict__ Q) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || __float_as_int(Q[i].z) != MAT_FLUID) return;
+    float4 p = P[i], v = V[i];
+    apply_walls(sp, p, v);
+    P[i] = p; V[i] = v;
+}
+
 // a = g - non-pressure sums + pressure sums; advert; walls
 // (wcsphv2.py:89-93, :53, :95-100 ; sph_basev2.py:151-189)
 __device__ __forceinline__ void force_epilogue(const SimParams& sp, int i, bool walker, float4 pi, float4 vi,
@@ -114,21 +143,8 @@ __device__ __forceinline__ void force_epilogue(const SimParams& sp, int i, bool 
         }
         acc.x = nx + apx; acc.y = ny + apy; acc.z = nz + apz;
         vout.x = vi.x + sp.dt * acc.x; vout.y = vi.y + sp.dt * acc.y; vout.z = vi.z + sp.dt * acc.z;
-        float px = pi.x + sp.dt * vout.x, py = pi.y + sp.dt * vout.y, pz = pi.z + sp.dt * vout.z;
-        float cnx = 0.f, cny = 0.f, cnz = 0.f;       // the wall tests use the pre-clamp position
-        pout.x = px; pout.y = py; pout.z = pz;
-        if (px > sp.wall_hi[0]) { cnx += 1.f; pout.x = sp.wall_hi[0]; }
-        if (px <= sp.pad)       { cnx -= 1.f; pout.x = sp.pad; }
-        if (py > sp.wall_hi[1]) { cny += 1.f; pout.y = sp.wall_hi[1]; }
-        if (py <= sp.pad)       { cny -= 1.f; pout.y = sp.pad; }
-        if (pz > sp.wall_hi[2]) { cnz += 1.f; pout.z = sp.wall_hi[2]; }
-        if (pz <= sp.pad)       { cnz -= 1.f; pout.z = sp.pad; }
-        float len = sqrtf(cnx * cnx + cny * cny + cnz * cnz);
-        if (len > 1e-6f) {
-            float ux = cnx / len, uy = cny / len, uz = cnz / len;
-            float sdot = 1.5f * (vout.x * ux + vout.y * uy + vout.z * uz);   // :151-156
-            vout.x -= sdot * ux; vout.y -= sdot * uy; vout.z -= sdot * uz;
-        }
+        pout.x = pi.x + sp.dt * vout.x; pout.y = pi.y + sp.dt * vout.y; pout.z = pi.z + sp.dt * vout.z;
+        if (sp.walls) apply_walls(sp, pout, vout);
     } else if (a_np_out) {
         a_np_out[i] = acc;
         a_p_out[i] = acc;

@@ -17,6 +17,8 @@ _FIELD_SPEC = {   # field -> (dtype, components: 'dim' | int | 'color' | 'cell')
     _capi.F_ORIG_ID: (np.int32, 1), _capi.F_A_NONPRESSURE: (np.float32, "dim"),
     _capi.F_A_PRESSURE: (np.float32, "dim"), _capi.F_CELL_COUNT: (np.int32, "cell"),
     _capi.F_NEIGHBORS: (np.int32, 100),
+    _capi.F_X_IN: (np.float32, "dim"), _capi.F_V_IN: (np.float32, "dim"),
+    _capi.F_PRESSURE_STORED: (np.float32, 1), _capi.F_PARTICLE_INDEX: (np.int32, 1),
 }
 
 

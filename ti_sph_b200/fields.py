@@ -15,8 +15,15 @@ _ZERO_COPY = (K.F_X, K.F_V, K.F_D_VELOCITY)
 class FieldView:
     def __init__(self, owner, field, name):
         self._owner = owner          # object with an `.engine`
-        self._field = field
+        self._field0 = field
         self.name = name
+
+    @property
+    def _field(self):
+        """the library field behind this view: while a step is driven kernel by kernel the owner
+        redirects some names to what the reference's field holds between those kernels"""
+        override = getattr(self._owner, "_field_override", None)
+        return self._field0 if override is None else override(self.name, self._field0)
 
     @property
     def _eng(self):
@@ -49,10 +56,15 @@ class FieldView:
     def __cuda_array_interface__(self):
         if self._field not in _ZERO_COPY:
             raise AttributeError(f"{self.name} has no zero-copy device view; use to_numpy()")
+        # The engine runs on its own non-blocking stream and step() is asynchronous: a consumer on another
+        # stream (torch's default, ggui) must not read records the force kernel is still writing.  The
+        # step is therefore completed before the pointer is handed out (CAI v3 "stream": None = the data is
+        # ready, no further synchronisation is needed).
+        self._eng.sync()
         ptr, stride = self._eng.device_ptr(self._field)
         n = self._eng.particle_num
         return {"shape": (n, self._eng.dim), "typestr": "<f4", "data": (ptr, False),
-                "strides": (stride, 4), "version": 3}
+                "strides": (stride, 4), "version": 3, "stream": None}
 
     def to_torch(self, device=None):
         import torch
