@@ -188,6 +188,16 @@ class ParticleSystemV4:
                 'material': e.download(K.F_MATERIAL, out.get('material')),
                 'color': e.download(K.F_COLOR, out.get('color'))}
 
+    def dump_async(self, out):
+        """dump() that does not wait (extension): starts filling the preallocated -- ideally page-locked --
+        arrays out['position'|'velocity'|'material'|'color'] and returns; dump_wait() completes them.  The copies
+        run on the engine's copy stream, next to the following steps."""
+        self.engine.dump_async(out.get('position'), out.get('velocity'), out.get('material'), out.get('color'))
+        return out
+
+    def dump_wait(self):
+        self.engine.dump_wait()
+
     def is_valid_cell(self, cell):
         return all(0 <= cell[i] < self.grid_num[i] for i in range(self.dim))
 

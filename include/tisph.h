@@ -191,6 +191,18 @@ int tisph_stage_run(tisph_ctx *ctx, int32_t stage);
 int tisph_download(tisph_ctx *ctx, int32_t field, void *dst, size_t bytes);
 /* Overwrite x and v of the current particles (current order) from host arrays [n][dim]. */
 int tisph_upload_xv(tisph_ctx *ctx, const float *pos, const float *vel);
+/* The same two transfers without blocking the host or the step: the host->device copy runs on a copy
+ * stream of the context (it overlaps the kernels already queued), the dump is one packing kernel plus
+ * device->host copies on a second copy stream.  Host arrays must be page-locked for the copies to be
+ * asynchronous, and must stay untouched until consumed: `pos`/`vel` of an upload until the next call
+ * that synchronises (tisph_sync, tisph_dump_wait after a later dump), the destinations of a dump until
+ * tisph_dump_wait (or the next tisph_dump_async, which waits for the previous one first).
+ * tisph_dump_async fills what ParticleSystemV4.dump() returns (partice_systemv4.py:279-296): position,
+ * velocity [n][dim] f32, material [n] i32, colour [n][3] (gen-2) / [n] (gen-1) i32, plus the original ids
+ * [n] i32; any destination may be NULL. */
+int tisph_upload_xv_async(tisph_ctx *ctx, const float *pos, const float *vel);
+int tisph_dump_async(tisph_ctx *ctx, float *pos, float *vel, int32_t *material, int32_t *color, int32_t *orig_id);
+int tisph_dump_wait(tisph_ctx *ctx);
 /* Zero-copy hand-off (ggui scene.particles(ps.x), torch, cupy): device pointer of the packed
  * float4 arrays {x,y,z,mass} (TISPH_F_X) / {vx,vy,vz,volume} (TISPH_F_V) / {ax,ay,az,0}
  * (TISPH_F_D_VELOCITY); valid until the next step. */

@@ -132,3 +132,36 @@ def test_cfl_time_step_extension():
     eng.set_param(K.P_CFL, 0.0)                                     # back to the reference's fixed step
     assert eng.get_param(K.P_DT) == pytest.approx(2e-4)
     eng.close()
+
+
+def test_asynchronous_upload_and_dump_match_the_blocking_calls():
+    """tisph_upload_xv_async / tisph_dump_async / tisph_dump_wait (pinned host arrays, copy streams) against
+    upload_xv / dump(), pipelined over a few steps the way bench.py's e2e loop uses them"""
+    import torch
+    from core.partice_system.partice_systemv4 import ParticleSystemV4
+    from core.sph.wcsphv2 import WCSPHV2
+    scene = small_scene(end=(0.5, 0.3, 0.9))
+    ps_a, ps_b = ParticleSystemV4(copy.deepcopy(scene)), ParticleSystemV4(copy.deepcopy(scene))
+    sa, sb = WCSPHV2(ps_a), WCSPHV2(ps_b)
+    n = ps_a.particle_num[None]
+    pin = lambda shape, dt: torch.empty(shape, dtype=dt).pin_memory().numpy()
+    hx, hv = pin((n, 3), torch.float32), pin((n, 3), torch.float32)
+    outs = {"position": pin((n, 3), torch.float32), "velocity": pin((n, 3), torch.float32),
+            "material": pin((n,), torch.int32), "color": pin((n, 3), torch.int32)}
+    d = ps_b.dump()
+    for step in range(4):
+        hx[:] = d["position"]; hv[:] = d["velocity"] * np.float32(1.0 + 0.01 * step)
+        ps_a.engine.upload_xv_async(hx, hv)
+        sa.step()
+        ps_a.dump_async(outs)
+        ps_b.engine.upload_xv(hx.copy(), hv.copy())
+        sb.step()
+        d = ps_b.dump()
+        ps_a.dump_wait()
+        for k in ("position", "velocity", "material", "color"):
+            assert np.array_equal(outs[k], d[k]), (step, k)
+    ids = pin((n,), torch.int32)
+    ps_a.engine.dump_async(orig_id=ids)
+    ps_a.engine.sync()                                       # sync() completes a pending dump too
+    assert np.array_equal(ids, ps_b.engine.download(K.F_ORIG_ID))
+    ps_a.engine.close(); ps_b.engine.close()

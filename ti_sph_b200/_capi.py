@@ -66,6 +66,9 @@ SYMBOLS = {
     "tisph_stage_run": (C.c_int, [_vp, _i32]),
     "tisph_download": (C.c_int, [_vp, _i32, _vp, C.c_size_t]),
     "tisph_upload_xv": (C.c_int, [_vp, _vp, _vp]),
+    "tisph_upload_xv_async": (C.c_int, [_vp, _vp, _vp]),
+    "tisph_dump_async": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp]),
+    "tisph_dump_wait": (C.c_int, [_vp]),
     "tisph_device_ptr": (C.c_int, [_vp, _i32, C.POINTER(_vp), _ip]),
     "tisph_set_param": (C.c_int, [_vp, _i32, C.c_double]),
     "tisph_get_param": (C.c_int, [_vp, _i32, C.POINTER(C.c_double)]),

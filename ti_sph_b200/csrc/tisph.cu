@@ -79,6 +79,12 @@ struct tisph_ctx {
     int grid_dl = 0, grid_fl = 0, grid_dfb = 0, grid_ffb = 0;   // persistent grids (SMs x resident CTAs)
     void* staging = nullptr;
     size_t staging_bytes = 0;
+    // asynchronous host <-> device path (tisph_upload_xv_async / tisph_dump_async): two copy streams and their
+    // own staging blocks, so that the copies of step k+1 / step k overlap each other and the kernels
+    cudaStream_t copy_in = nullptr, copy_out = nullptr;
+    cudaEvent_t ev_in_done = nullptr, ev_in_free = nullptr, ev_out_ready = nullptr, ev_out_done = nullptr;
+    void *ain = nullptr, *aout = nullptr;
+    bool out_pending = false;
     float4 *snapP = nullptr, *snapV = nullptr, *snapQ = nullptr;   // tisph_state_save
     int snap_n = -1;
     int diagnostics = 0;
@@ -493,6 +499,13 @@ int tisph_destroy(tisph_ctx* c) {
     cudaFree(c->keys_sorted); cudaFree(c->cell_count); cudaFree(c->cell_end);
     cudaFree(c->snapP); cudaFree(c->snapV); cudaFree(c->snapQ);
     cudaFree(c->block_sums); cudaFree(c->color); cudaFree(c->err_dev); cudaFree(c->staging);
+    if (c->copy_in) {
+        cudaStreamSynchronize(c->copy_in); cudaStreamSynchronize(c->copy_out);
+        cudaEventDestroy(c->ev_in_done); cudaEventDestroy(c->ev_in_free);
+        cudaEventDestroy(c->ev_out_ready); cudaEventDestroy(c->ev_out_done);
+        cudaStreamDestroy(c->copy_in); cudaStreamDestroy(c->copy_out);
+        cudaFree(c->ain); cudaFree(c->aout);
+    }
     cudaFree(c->items); cudaFree(c->ctr); cudaFree(c->fb_d); cudaFree(c->fb_f); cudaFree(c->item_flags);
     cudaFree(c->Lg); cudaFree(c->item_row);
     cudaFree(c->rank_key); cudaFree(c->range_dev); cudaFree(c->shard_ctr);
@@ -701,6 +714,7 @@ static int check_device_errors(tisph_ctx* c) {
 
 int tisph_sync(tisph_ctx* c) {
     CHECK_CTX(c);
+    { int rc = tisph_dump_wait(c); if (rc) return rc; }
     CU(cudaStreamSynchronize(c->stream));
     return check_device_errors(c);
 }
@@ -789,6 +803,85 @@ int tisph_upload_xv(tisph_ctx* c, const float* pos, const float* vel) {
     k_upload_xv<<<nblocks(n, 256), 256, 0, st>>>(n, dim, d_pos, d_vel, c->P[c->cur] + c->o_lo, c->V[c->cur] + c->o_lo);
     c->launches += 1;
     CU(cudaGetLastError());
+    return TISPH_OK;
+}
+
+// ---- asynchronous host <-> device path -----------------------------------------------------------
+static int async_setup(tisph_ctx* c) {
+    if (c->copy_in) return TISPH_OK;
+    CU(cudaStreamCreateWithFlags(&c->copy_in, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&c->copy_out, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&c->ev_in_done, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&c->ev_in_free, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&c->ev_out_ready, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&c->ev_out_done, cudaEventDisableTiming));
+    CU(cudaMalloc(&c->ain, (size_t)c->cap * 24));           // x | v
+    CU(cudaMalloc(&c->aout, (size_t)c->cap * 44));          // x | v | material | colour | orig_id
+    CU(cudaEventRecord(c->ev_in_free, c->stream));
+    return TISPH_OK;
+}
+
+int tisph_upload_xv_async(tisph_ctx* c, const float* pos, const float* vel) {
+    CHECK_CTX(c);
+    if (!pos || !vel) return fail(TISPH_ERR_INVALID, "null argument");
+    if (c->phase != 0 || c->uphase != 0 || c->appended) return fail(TISPH_ERR_INVALID, "cannot upload in the middle of a step");
+    { int rc = ensure_range(c); if (rc) return rc; }
+    { int rc = async_setup(c); if (rc) return rc; }
+    int n = c->o_hi - c->o_lo, dim = c->cfg.dim;
+    if (n == 0) return TISPH_OK;
+    float* d_pos = (float*)c->ain;
+    float* d_vel = d_pos + (size_t)n * dim;
+    CU(cudaStreamWaitEvent(c->copy_in, c->ev_in_free, 0));          // the previous upload's kernel has read the block
+    CU(cudaMemcpyAsync(d_pos, pos, (size_t)n * dim * 4, cudaMemcpyHostToDevice, c->copy_in));
+    CU(cudaMemcpyAsync(d_vel, vel, (size_t)n * dim * 4, cudaMemcpyHostToDevice, c->copy_in));
+    CU(cudaEventRecord(c->ev_in_done, c->copy_in));
+    CU(cudaStreamWaitEvent(c->stream, c->ev_in_done, 0));
+    k_upload_xv<<<nblocks(n, 256), 256, 0, c->stream>>>(n, dim, d_pos, d_vel, c->P[c->cur] + c->o_lo, c->V[c->cur] + c->o_lo);
+    c->launches += 1;
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(c->ev_in_free, c->stream));
+    return TISPH_OK;
+}
+
+int tisph_dump_wait(tisph_ctx* c) {
+    CHECK_CTX(c);
+    if (c->out_pending) {
+        CU(cudaEventSynchronize(c->ev_out_done));
+        c->out_pending = false;
+    }
+    return TISPH_OK;
+}
+
+int tisph_dump_async(tisph_ctx* c, float* pos, float* vel, int32_t* material, int32_t* color, int32_t* orig_id) {
+    CHECK_CTX(c);
+    if (c->phase != 0 || c->uphase != 0 || c->appended) return fail(TISPH_ERR_INVALID, "cannot dump in the middle of a step");
+    if (color && c->sharded) return fail(TISPH_ERR_INVALID, "colour is kept by the host side of a sharded run");
+    { int rc = ensure_range(c); if (rc) return rc; }
+    { int rc = async_setup(c); if (rc) return rc; }
+    { int rc = tisph_dump_wait(c); if (rc) return rc; }               // the staging block and the host arrays are free again
+    const int n = c->o_hi - c->o_lo, dim = c->cfg.dim, cc = c->color_comp, cur = c->cur;
+    if (n == 0) return TISPH_OK;
+    char* s = (char*)c->aout;
+    float* o_x = (float*)s;  s += (size_t)n * dim * 4;
+    float* o_v = (float*)s;  s += (size_t)n * dim * 4;
+    int* o_m = (int*)s;      s += (size_t)n * 4;
+    int* o_c = (int*)s;      s += (size_t)n * cc * 4;
+    int* o_i = (int*)s;
+    k_dump_pack<<<nblocks(n, 256), 256, 0, c->stream>>>(n, dim, cc, c->P[cur] + c->o_lo, c->V[cur] + c->o_lo,
+                                                        c->Q[cur] + c->o_lo, c->color, pos ? o_x : nullptr, vel ? o_v : nullptr,
+                                                        material ? o_m : nullptr, color ? o_c : nullptr, orig_id ? o_i : nullptr);
+    c->launches += 1;
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(c->ev_out_ready, c->stream));
+    CU(cudaStreamWaitEvent(c->copy_out, c->ev_out_ready, 0));
+    if (pos) CU(cudaMemcpyAsync(pos, o_x, (size_t)n * dim * 4, cudaMemcpyDeviceToHost, c->copy_out));
+    if (vel) CU(cudaMemcpyAsync(vel, o_v, (size_t)n * dim * 4, cudaMemcpyDeviceToHost, c->copy_out));
+    if (material) CU(cudaMemcpyAsync(material, o_m, (size_t)n * 4, cudaMemcpyDeviceToHost, c->copy_out));
+    if (color) CU(cudaMemcpyAsync(color, o_c, (size_t)n * cc * 4, cudaMemcpyDeviceToHost, c->copy_out));
+    if (orig_id) CU(cudaMemcpyAsync(orig_id, o_i, (size_t)n * 4, cudaMemcpyDeviceToHost, c->copy_out));
+    CU(cudaEventRecord(c->ev_out_done, c->copy_out));
+    // the next kernel that writes the staging block is the next tisph_dump_async's, which waits above
+    c->out_pending = true;
     return TISPH_OK;
 }
 

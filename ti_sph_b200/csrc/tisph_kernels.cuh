@@ -293,6 +293,28 @@ k_unpack(int n, const float4* __restrict__ src, int comp0, int ncomp, uint32_t* 
     for (int k = 0; k < ncomp; ++k) dst[(size_t)i * ncomp + k] = w[comp0 + k];
 }
 
+// dump() in one launch: x | v | material | colour (through orig_id) | orig_id of n particles, each in the
+// reference's layout, into one staging block (any destination may be null)
+__global__ void __launch_bounds__(256)
+k_dump_pack(int n, int dim, int ncolor, const float4* __restrict__ P, const float4* __restrict__ V,
+            const float4* __restrict__ Q, const int* __restrict__ color, float* __restrict__ out_x,
+            float* __restrict__ out_v, int* __restrict__ out_mat, int* __restrict__ out_col,
+            int* __restrict__ out_id) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 p = P[i], v = V[i], q = Q[i];
+    const float pw[3] = {p.x, p.y, p.z}, vw[3] = {v.x, v.y, v.z};
+    for (int k = 0; k < dim; ++k) {
+        if (out_x) out_x[(size_t)i * dim + k] = pw[k];
+        if (out_v) out_v[(size_t)i * dim + k] = vw[k];
+    }
+    if (out_mat) out_mat[i] = __float_as_int(q.z);
+    const int id = __float_as_int(q.w);
+    if (out_id) out_id[i] = id;
+    if (out_col)
+        for (int k = 0; k < ncolor; ++k) out_col[(size_t)i * ncolor + k] = color[(size_t)id * ncolor + k];
+}
+
 // max |v|^2 over the fluid particles, as float bits (non-negative floats order like unsigned ints):
 // input of the optional CFL time step (an extension; the reference's dt is fixed, sph_basev2.py:14-15)
 __global__ void __launch_bounds__(256)

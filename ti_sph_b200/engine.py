@@ -84,6 +84,27 @@ class Engine:
         vel = np.ascontiguousarray(vel, np.float32).reshape(n, self.dim)
         check(self._lib.tisph_upload_xv(self._ctx, _ptr(pos), _ptr(vel)))
 
+    def upload_xv_async(self, pos, vel):
+        """upload_xv without blocking: `pos` / `vel` must be C-contiguous f32 [n][dim] (page-locked for a truly
+        asynchronous copy) and stay untouched until the engine is synchronised"""
+        n = self.particle_num
+        assert pos.dtype == np.float32 and vel.dtype == np.float32 and pos.flags.c_contiguous and vel.flags.c_contiguous
+        assert pos.size == n * self.dim and vel.size == n * self.dim
+        check(self._lib.tisph_upload_xv_async(self._ctx, _ptr(pos), _ptr(vel)))
+
+    def dump_async(self, position=None, velocity=None, material=None, color=None, orig_id=None):
+        """start filling the given preallocated host arrays (any subset) with the current state; they are
+        complete after dump_wait()"""
+        n = self.particle_num
+        for a, dt, cols in ((position, np.float32, self.dim), (velocity, np.float32, self.dim), (material, np.int32, 1),
+                            (color, np.int32, 3 if self.generation == 2 else 1), (orig_id, np.int32, 1)):
+            assert a is None or (a.dtype == dt and a.flags.c_contiguous and a.size == n * cols)
+        check(self._lib.tisph_dump_async(self._ctx, _ptr(position), _ptr(velocity), _ptr(material), _ptr(color),
+                                         _ptr(orig_id)))
+
+    def dump_wait(self):
+        check(self._lib.tisph_dump_wait(self._ctx))
+
     # -- stepping ----------------------------------------------------------------------
     def step(self, nsteps=1):
         check(self._lib.tisph_step(self._ctx, int(nsteps)))

@@ -438,6 +438,18 @@ class ShardedSim:
         """overwrite x, v of this rank's owned particles (order of dump_local) from host arrays"""
         self.engine.upload_xv(pos, vel)
 
+    def upload_xv_async(self, pos, vel):
+        self.engine.upload_xv_async(pos, vel)
+
+    def dump_local_async(self, out):
+        """dump_local without waiting: starts filling out['position'|'velocity'|'material'|'orig_id'] (preallocated,
+        sized for this rank's owned particles); complete after dump_wait()"""
+        self.engine.dump_async(out.get("position"), out.get("velocity"), out.get("material"), None, out.get("orig_id"))
+        return out
+
+    def dump_wait(self):
+        self.engine.dump_wait()
+
     def dump_local(self, out=None, color=True):
         """this rank's owned particles, in sorted order (keys of dump() + 'orig_id'); `out` may hold
         preallocated (pinned) arrays for 'position', 'velocity', 'material', 'orig_id'.  The colour is a host-side
