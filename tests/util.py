@@ -123,3 +123,22 @@ def golden_gen2_force_reference(case, z, s=0):
     return {"mag_nonpressure": mnp, "mag_pressure": mp, "mag_pressure_floor": mpf, "a_nonpressure": a_np_ref,
             "a_pressure": a_ref - a_np_ref, "d_velocity": a_ref, "material": g("sorted.material"),
             "v": g("end.v"), "x": g("end.x")}
+
+
+def check_end_state(x, v, t, dt=2e-4, rtol=RTOL):
+    """x, v after a whole step against a traced oracle step `t` (rows in the oracle's order): the same
+    bounds check_force_stage puts on v' and x'"""
+    mnp, mp = t["mag_nonpressure"].astype(np.float64), t["mag_pressure"].astype(np.float64)
+    pf = t["mag_pressure_floor"].astype(np.float64) + rtol * mp
+    fl = t["material"] == 1
+    mag, pf = (mnp + mp)[fl], pf[fl]
+    dv = np.linalg.norm(np.asarray(v, np.float64)[fl] - t["v"][fl], axis=1)
+    vn = np.linalg.norm(t["v"][fl].astype(np.float64), axis=1)
+    dx = np.linalg.norm(np.asarray(x, np.float64)[fl] - t["x"][fl], axis=1)
+    xn = np.linalg.norm(t["x"][fl].astype(np.float64), axis=1)
+    worst = {"v": float(np.max(np.maximum(dv - dt * pf, 0.0) / (vn + dt * mag))),
+             "x": float(np.max(np.maximum(dx - dt * dt * pf, 0.0) / (xn + dt * vn + dt * dt * mag)))}
+    bad = {k: w for k, w in worst.items() if not w < rtol}
+    assert not bad, f"beyond {rtol:g} relative: {bad}"
+    assert np.array_equal(np.asarray(x)[~fl], t["x"][~fl]) and np.array_equal(np.asarray(v)[~fl], t["v"][~fl])
+    return worst

@@ -236,7 +236,7 @@ k_density_list(SimParams sp, const int* __restrict__ cell_end, const int2* __res
             int cnt = 0;
             // the filter thread of (target tD, lane j) was thread 32 j + tD
             const uint32_t nab = LC[32 * j + tD];
-            const uint32_t nA = nab & 0xffu, nB = nab >> 8;
+            uint32_t nA = nab & 0xffu, nB = nab >> 8;
             if (self_s >= 0 && (self_s & 7) == j) {
                 // p_i != p_j (partice_systemv4.py:344): the target itself passed the filter (d2 = 0).  Its stream
                 // is ascending, so a binary search finds the entry; the stream's dummy row takes its place.
@@ -250,9 +250,9 @@ k_density_list(SimParams sp, const int* __restrict__ cell_end, const int2* __res
                 TISPH_CHECK(lo < ((ms & 1u) ? nB : nA) && lds_u8(sb + 2u * lo) == ms);
                 sts_u8(sb + 2u * lo, M_DUMMY + (ms & 1u));
             }
-            // pad both streams with their dummy row to the longest list of the warp (a whole number of words),
-            // then one (first, second) pair of entries per iteration, branch-free
-            const uint32_t n2 = (2u * max(nA, nB) + 2u) & ~3u;                  // 2 x pairs I hand to the force walk
+            // pad both streams with their dummy row to the longest list of the warp, then one (first, second)
+            // pair of entries per iteration, branch-free
+            const uint32_t n2 = (2u * max(nA, nB) + 2u) & ~3u;
             const uint32_t nmax = __reduce_max_sync(0xffffffffu, n2);
             for (uint32_t k = 2u * nA; k < nmax; k += 2u) sts_u8(sL + offA + k, M_DUMMY);
             for (uint32_t k = 2u * nB; k < nmax; k += 2u) sts_u8(sL + offB + k, M_DUMMY + 1);
@@ -300,7 +300,16 @@ k_density_list(SimParams sp, const int* __restrict__ cell_end, const int2* __res
             // ---- hand my pairs to the force walk: the warp reserves a count row and the rows of its longest
             //      lane (rows of 32 words), then copies whole words of (first, second, first, second) entries
             if (own) {
-                const int nw = (int)(n2 >> 2);
+                // The force walk consumes the two streams in lockstep, so the longer one sets its number of
+                // iterations: level them by moving tail entries across (there the parity only matters for the
+                // banks: an entry in the "wrong" stream costs its gathers a two-way conflict; ~1 in 10 moves),
+                // then pad to a whole number of words.
+                while (nA > nB + 1u) { --nA; sts_u8(sL + offB + 2u * nB, lds_u8(sL + offA + 2u * nA)); ++nB; }
+                while (nB > nA + 1u) { --nB; sts_u8(sL + offA + 2u * nA, lds_u8(sL + offB + 2u * nB)); ++nA; }
+                const uint32_t n2f = (2u * max(nA, nB) + 2u) & ~3u;             // 2 x pairs I hand to the force walk
+                for (uint32_t k = 2u * nA; k < n2f; k += 2u) sts_u8(sL + offA + k, M_DUMMY);
+                for (uint32_t k = 2u * nB; k < n2f; k += 2u) sts_u8(sL + offB + k, M_DUMMY + 1);
+                const int nw = (int)(n2f >> 2);
                 const int rows = __reduce_max_sync(0xffffffffu, nw) + 1;
                 int row = 0;
                 if (lane == 0) {

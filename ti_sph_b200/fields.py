@@ -72,15 +72,23 @@ class FieldView:
 
     def to_taichi(self):
         """mirror into a Taichi field (kept and refilled on later calls, so that a GUI loop such as
-        main_3d.py:41 `scene.particles(ps.x, ...)` does not allocate a field per frame)"""
+        main_3d.py:41 `scene.particles(ps.x, ...)` does not allocate a field per frame).  Fields with a
+        device view (x, v, d_velocity) are refilled device to device through `field.from_torch` -- no host
+        round trip; the others, and Taichi builds without torch interop, go through numpy."""
         import taichi as ti     # optional: only for the ggui hand-off
-        a = self.to_numpy()
+        shape = self._eng.field_shape(self._field)[1]
         f = getattr(self, "_ti_field", None)
-        if f is None or tuple(f.shape) != a.shape[:1]:
-            dt = ti.f32 if a.dtype == np.float32 else ti.i32
-            f = ti.Vector.field(a.shape[1], dtype=dt, shape=a.shape[0]) if a.ndim == 2 else ti.field(dtype=dt, shape=a.shape[0])
+        if f is None or tuple(f.shape) != tuple(shape[:1]):
+            dt = ti.f32 if self.dtype == np.float32 else ti.i32
+            f = ti.Vector.field(shape[1], dtype=dt, shape=shape[0]) if len(shape) == 2 else ti.field(dtype=dt, shape=shape[0])
             self._ti_field = f
-        f.from_numpy(a)
+        if self._field in _ZERO_COPY and hasattr(f, "from_torch"):
+            try:
+                f.from_torch(self.to_torch().contiguous())       # strided float4 view -> packed [n][dim], on the device
+                return f
+            except Exception:
+                pass
+        f.from_numpy(self.to_numpy())
         return f
 
 

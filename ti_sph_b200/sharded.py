@@ -251,6 +251,14 @@ class ShardedSim:
         self.torch = torch
         self.rank, self.world, self.comm = rank, world, comm
         self.scene = scene
+        if scene["rigidBodies"] and len(rigid_points) != len(scene["rigidBodies"]):
+            if len(rigid_points):
+                raise ValueError(f"{len(scene['rigidBodies'])} rigid bodies but {len(rigid_points)} point sets")
+            # like ParticleSystemV4.load_rigid_body: every rank voxelises the bodies itself (same result on every
+            # rank).  Within a body the original ids follow the x-planes (SceneParts), not the sampler's order.
+            from . import mesh
+            pitch = 2 * scene["configuration"]["particleRadius"]
+            rigid_points = [mesh.sample_rigid_body(dict(body), pitch, device=device) for body in scene["rigidBodies"]]
         self.parts = SceneParts(scene, rigid_points)
         self.ghost = 1 if (density_mode == "reference" and volume_mode == "reference") else 2
         counts = self.parts.plane_counts()
@@ -377,6 +385,20 @@ class ShardedSim:
             t3 = time.perf_counter()
             for k, v in (("pack", t1 - t0), ("exchange", t2 - t1), ("compute_issue", t3 - t2), ("steps", 1)):
                 self.profile[k] = self.profile.get(k, 0.0) + v
+
+    def set_cfl(self, cfl):
+        """One CFL step for all ranks (extension; TISPH_P_CFL itself is per context and refused on a sharded
+        one): dt = min(dt0, cfl h / (c_s + max |v|)) with the maximum taken over every rank.  Collective;
+        call between steps, as often as the step should follow the flow."""
+        vmax = max(self.comm.all_gather_objects(self.engine.get_param(K.P_MAX_SPEED))) if self.comm else \
+            self.engine.get_param(K.P_MAX_SPEED)
+        cfg = self.scene["configuration"]
+        dt0 = getattr(self, "_dt0", None)
+        if dt0 is None:
+            dt0 = self._dt0 = self.engine.get_param(K.P_DT)
+        dt = min(dt0, cfl * 4.0 * cfg["particleRadius"] / (cfg["c_s"] + vmax))
+        self.engine.set_param(K.P_DT, dt)
+        return dt
 
     # -- re-balancing --------------------------------------------------------------------------
     def owned_plane_counts(self):
