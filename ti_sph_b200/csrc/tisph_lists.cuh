@@ -71,6 +71,9 @@ __device__ __forceinline__ int slot_to_cand(int s) {
 __device__ __forceinline__ void sts_u8(uint32_t a, uint32_t v) {
     asm volatile("st.shared.u8 [%0], %1;" :: "r"(a), "r"(v) : "memory");
 }
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+    asm volatile("prefetch.global.L2 [%0];" :: "l"(p));
+}
 __device__ __forceinline__ uint32_t lds_u8(uint32_t a) {
     uint32_t v;
     asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
@@ -116,9 +119,11 @@ k_density_list(SimParams sp, const int* __restrict__ cell_end, const int2* __res
     unsigned short* LC = reinterpret_cast<unsigned short*>(L + GL * LIST_J * 4);     // entries per stream: nA | nB << 8
     int* GM = reinterpret_cast<int*>(LC + NB_THREADS);
     __shared__ CellRanges R;
-    __shared__ int s_slot, s_over;
+    __shared__ ItemMeta M;
+    __shared__ int s_over;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n_items = ctr->n_items;
     const float cut_wide = sp.d2_cut * 1.000001f;          // superset filter; the drain applies the exact test
     const float2 one2 = make_float2(sp.one, sp.one);       // see the drain: keeps ptxas from contracting the exact sum
     // ---- filter arrangement: lane jF = warp, target tF = lane
@@ -140,11 +145,17 @@ k_density_list(SimParams sp, const int* __restrict__ cell_end, const int2* __res
     if (tid < 8) { FXY[8 * (LT_ROWS - 1) + tid] = make_float4(-FAR, -FAR, -FAR, -FAR); FZ[8 * (LT_ROWS - 1) + tid] = make_float2(-FAR, -FAR); }
     if (AKINCI && tid < 16) GM[8 * M_DUMMY + tid] = MAT_FLUID;
 
+    ItemFetch nx;
+    if (warp == 0) nx = fetch_item(sp, cell_end, items, n_items, &ctr->work_d);
     for (;;) {
-        const int it = next_item(&ctr->work_d, &s_slot);
-        if (it >= ctr->n_items) break;
+        __syncthreads();                                   // everyone is done with the previous item's shared state
+        if (warp == 0) publish_item(nx, R, M);
+        __syncthreads();
+        const int it = M.it;
+        if (it >= n_items) break;
         ItemGeom G;
-        item_setup(sp, cell_end, items[it], R, G);
+        item_geometry(M, R, G);
+        if (warp == 0) nx = fetch_item(sp, cell_end, items, n_items, &ctr->work_d);   // the next item, behind this one's walk
         if (G.total > LT_CAP || all_to_fallback) {          // a candidate's row must fit one byte
             if (tid == 0) {
                 flags[it] = 2;
@@ -304,8 +315,19 @@ k_density_list(SimParams sp, const int* __restrict__ cell_end, const int2* __res
                 // iterations: level them by moving tail entries across (there the parity only matters for the
                 // banks: an entry in the "wrong" stream costs its gathers a two-way conflict; ~1 in 10 moves),
                 // then pad to a whole number of words.
-                while (nA > nB + 1u) { --nA; sts_u8(sL + offB + 2u * nB, lds_u8(sL + offA + 2u * nA)); ++nB; }
-                while (nB > nA + 1u) { --nB; sts_u8(sL + offA + 2u * nA, lds_u8(sL + offB + 2u * nB)); ++nA; }
+                {
+                    const bool a_long = nA > nB;
+                    const uint32_t ns = a_long ? nA : nB, nd = a_long ? nB : nA;
+                    const uint32_t src = sL + (a_long ? offA : offB), dst = sL + (a_long ? offB : offA);
+                    const uint32_t mv = min(8u, (ns - nd) >> 1);                // (loads first: their latencies overlap)
+                    uint32_t e[8];
+#pragma unroll
+                    for (uint32_t u = 0; u < 8u; ++u) if (u < mv) e[u] = lds_u8(src + 2u * (ns - 1u - u));
+#pragma unroll
+                    for (uint32_t u = 0; u < 8u; ++u) if (u < mv) sts_u8(dst + 2u * (nd + u), e[u]);
+                    nA = a_long ? ns - mv : nd + mv;
+                    nB = a_long ? nd + mv : ns - mv;
+                }
                 const uint32_t n2f = (2u * max(nA, nB) + 2u) & ~3u;             // 2 x pairs I hand to the force walk
                 for (uint32_t k = 2u * nA; k < n2f; k += 2u) sts_u8(sL + offA + k, M_DUMMY);
                 for (uint32_t k = 2u * nB; k < n2f; k += 2u) sts_u8(sL + offB + k, M_DUMMY + 1);
@@ -435,9 +457,10 @@ k_force_list(SimParams sp, const int* __restrict__ cell_end, const int2* __restr
     float2* V23 = V01 + LT_SLOTS;
     float* PR = reinterpret_cast<float*>(V23 + LT_SLOTS);
     __shared__ CellRanges R;
-    __shared__ int s_slot;
+    __shared__ ItemMeta M;
     const int tid = threadIdx.x;
     const int j = tid & (GL - 1);
+    const int n_items = ctr->n_items;
     const uint32_t sP = smem_u32(P01) + 8u * j, sR = smem_u32(PR) + 4u * j;
     const float nkdw_h = -sp.k_dw * sp.inv_h;
     if (tid < 16) {                                         // the two dummy rows: FAR away, for good
@@ -447,15 +470,24 @@ k_force_list(SimParams sp, const int* __restrict__ cell_end, const int2* __restr
         PR[s] = 0.f;
     }
 
+    ItemFetch nx;
+    if (tid < 32) nx = fetch_item(sp, cell_end, items, n_items, &ctr->work_f);
     for (;;) {
-        const int it = next_item(&ctr->work_f, &s_slot);
-        if (it >= ctr->n_items) break;
-        if (flags[it]) continue;                         // handled by k_force_fb
-        if (items[it].x < sp.own_key_lo || items[it].x >= sp.own_key_hi) continue;   // ghost cell: not advanced here
+        __syncthreads();                                 // everyone is done with the previous item's shared state
+        if (tid < 32) publish_item(nx, R, M);
+        __syncthreads();
+        const int it = M.it;
+        if (it >= n_items) break;
         ItemGeom G;
-        item_setup(sp, cell_end, items[it], R, G);
+        item_geometry(M, R, G);
+        if (tid < 32) nx = fetch_item(sp, cell_end, items, n_items, &ctr->work_f);   // the next item, behind this one's walk
+        if (flags[it]) continue;                         // handled by k_force_fb
+        if (G.c < sp.own_key_lo || G.c >= sp.own_key_hi) continue;   // ghost cell: not advanced here
         TISPH_CHECK(G.total <= LT_CAP);
         const int npass = (G.nT + PASS_T - 1) / PASS_T;
+        // my warp's rows of the list pool, one block per pass: asked for now, needed after the staging
+        const int row_p0 = item_row[(2 * it) * 8 + (tid >> 5)];
+        const int row_p1 = npass > 1 ? item_row[(2 * it + 1) * 8 + (tid >> 5)] : row_p0;
         // ---- stage the tile: candidate e in slot cand_to_slot(e); two candidates per thread and round,
         //      all eight loads in flight before the first store
         for (int e0 = tid; e0 < G.total; e0 += 2 * NB_THREADS) {
@@ -479,6 +511,15 @@ k_force_list(SimParams sp, const int* __restrict__ cell_end, const int2* __restr
                 PR[sl] = d1.y;
             }
         }
+        // the lists were written by the density walk long ago (DRAM): pull the count row and the first list rows
+        // of both passes into L2 while the tile is being staged
+        if (row_p0 >= 0 && row_p1 >= 0) {
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                prefetch_l2(Lg + (size_t)(row_p0 + r) * 32 + (tid & 31));
+                prefetch_l2(Lg + (size_t)(row_p1 + r) * 32 + (tid & 31));
+            }
+        }
         __syncthreads();
         for (int pass = 0; pass < npass; ++pass) {
             const int t_local = pass * PASS_T + (tid >> 3);
@@ -494,7 +535,7 @@ k_force_list(SimParams sp, const int* __restrict__ cell_end, const int2* __restr
             const float nub_i = sp.visc_bound_c / (2.0f * rho_i);     // wcsphv2.py:76
             ForceAcc2 A;
             A.anx = A.any = A.anz = A.apx = A.apy = A.apz = make_float2(0.f, 0.f);
-            const int row = item_row[(2 * it + pass) * 8 + (tid >> 5)];     // my warp's rows of the list pool
+            const int row = pass ? row_p1 : row_p0;
             TISPH_CHECK(row >= 0);
             const uint32_t* gl = Lg + (size_t)row * 32 + (tid & 31);
             const int nw = walker ? (int)gl[0] : 0;                   // words of 4 entries (count row)

@@ -191,6 +191,68 @@ __device__ __forceinline__ int next_item(int* cursor, int* s_slot) {
     return *s_slot;
 }
 
+// ---- item pipeline of the list kernels ----------------------------------------------------------
+// Fetching an item is a chain of dependent global accesses (cursor atomic -> item record -> cell_end
+// ranges).  Warp 0 therefore fetches item k+1 into registers right after item k has been published, so
+// that the chain runs behind item k's walk; two barriers per item publish it to the CTA.
+struct ItemFetch {
+    int it;         // item index (>= n_items: the list is exhausted)
+    int2 item;
+    int a, b;       // lane < 9: first sorted index / length of range `lane`;  lane 9: first / end index of the cell
+};
+struct ItemMeta { int it, cell, first, tb, te; };
+
+__device__ __forceinline__ ItemFetch fetch_item(const SimParams& sp, const int* __restrict__ cell_end,
+                                                const int2* __restrict__ items, int n_items, int* cursor) {
+    const int lane = threadIdx.x & 31;
+    ItemFetch f;
+    int it = 0;
+    if (lane == 0) it = atomicAdd(cursor, 1);
+    f.it = __shfl_sync(0xffffffffu, it, 0);
+    f.item = make_int2(0, 0);
+    f.a = f.b = 0;
+    if (f.it < n_items) {
+        f.item = items[f.it];
+        const int c = f.item.x;
+        if (lane < 9) {
+            const int cz = c % sp.gz, cy = (c / sp.gz) % sp.gy, cx = c / (sp.gz * sp.gy);
+            const int x = cx + lane / 3 - 1, y = cy + lane % 3 - 1;
+            if (x >= 0 && x < sp.gx && y >= 0 && y < sp.gy) {
+                const int zlo = max(cz - 1, 0), zhi = min(cz + 1, sp.gz - 1);
+                const int clo = (x * sp.gy + y) * sp.gz + zlo;
+                f.a = cell_end[max(clo - 1, 0)];
+                f.b = cell_end[clo + (zhi - zlo)] - f.a;
+            }
+        } else if (lane == 9) {
+            f.a = cell_start(cell_end, c);
+            f.b = cell_end[c];
+        }
+    }
+    return f;
+}
+
+// warp 0: make the fetched item the CTA's current one (the caller puts a barrier on either side)
+__device__ __forceinline__ void publish_item(const ItemFetch& f, CellRanges& R, ItemMeta& M) {
+    const int lane = threadIdx.x & 31;
+    const int len = lane < 9 ? f.b : 0;
+    const int inc = warp_inclusive_scan(len, lane);
+    if (lane < 9) { R.gb[lane] = f.a; R.off[lane] = inc - len; }
+    if (lane == 8) R.off[9] = inc;
+    if (lane == 9) { M.tb = f.a; M.te = f.b; }
+    if (lane == 0) { M.it = f.it; M.cell = f.item.x; M.first = f.item.y; }
+}
+
+__device__ __forceinline__ void item_geometry(const ItemMeta& M, const CellRanges& R, ItemGeom& G) {
+    G.c = M.cell;
+    G.tb = M.tb;
+    G.te = M.te;
+    G.i0 = G.tb + (M.first & ~ITEM_HALF);
+    G.nT = min(G.te - G.i0, (M.first & ITEM_HALF) ? 32 : 64);
+    G.tl = G.nT <= 32 ? 32 : 64;
+    G.nsplit = NB_THREADS / G.tl;
+    G.total = R.off[9];
+}
+
 // =======================================================================================
 // Small PTX helpers of the list kernels
 // =======================================================================================
