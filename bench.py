@@ -580,14 +580,20 @@ def main():
     ap.add_argument("--mode", default="reference", choices=["reference", "summed"],
                     help="density mode: reference = bit-faithful to wcsphv2.py:32-34, summed = intent")
     ap.add_argument("--e2e-steps", type=int, default=5)
-    ap.add_argument("--pre-steps", type=int, default=10, help="steps from the lattice before the state is saved")
-    ap.add_argument("--chain", type=int, default=5, help="steps per replay chain (main_3d.py renders every 5)")
+    ap.add_argument("--pre-steps", type=int, default=None,
+                    help="steps from the lattice before the state is saved (default: 10; 2 in summed mode, where the "
+                         "reference's fixed dt is beyond the CFL limit at r = 0.005 and the block disintegrates within ~10 steps)")
+    ap.add_argument("--chain", type=int, default=None, help="steps per replay chain (default 5, as main_3d.py renders every 5; 3 in summed mode)")
     ap.add_argument("--cpu-particles", type=int, default=1000000, help="size of the cpu_baseline sample")
     ap.add_argument("--ref-particles", type=int, default=1000000, help="sample size of --impl reference")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-also", action="store_true", help="skip the side measurements of the C5 run (1 M particles; summed mode)")
     ap.add_argument("--no-check", action="store_true", help="skip the sharded-vs-single-engine check of a multi-GPU run")
     args = ap.parse_args()
+    if args.pre_steps is None:
+        args.pre_steps = 2 if args.mode == "summed" else 10
+    if args.chain is None:
+        args.chain = 3 if args.mode == "summed" else 5
     if args.warmup < 3:
         log("[bench] warm-up raised to 3 (timing rules)")
         args.warmup = 3
