@@ -50,6 +50,27 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+_RESULT_FD = None
+
+
+def claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner on
+    stdout): from here on file descriptor 1 goes to stderr, and emit() writes the line to the real stdout."""
+    global _RESULT_FD
+    if _RESULT_FD is None:
+        sys.stdout.flush()
+        _RESULT_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, data)
+
+
 def measured_peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -196,7 +217,7 @@ def run_reference_impl(args):
         "note": "Taichi is not installable here, so the reference's own kernels cannot run; this is "
                 "the CPU restatement of them (oracle/sph_oracle.c, OpenMP over all host threads)",
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ----------------------------------------------------------------------------- GPU arm
@@ -417,28 +438,32 @@ def run_gpu(args):
         state = {"k": 0, "d": None}
 
         def dump_start():
-            k = eng.particle_num           # the owned set changes as particles migrate
+            k = eng.particle_num           # the owned set changes as particles migrate (this waits for the step)
             state["k"] += 1
             state["d"] = sim.dump_local_async(views(bufs[state["k"] & 1], k))
         dump_start()
         sim.dump_wait()
-        bytes_io = [0, 0]
+        k0 = eng.particle_num
+        hx0, hv0 = pinned((k0, 3), np.float32), pinned((k0, 3), np.float32)
+        hx0[:] = state["d"]["position"]; hv0[:] = state["d"]["velocity"]
+        bytes_io = [hx0.nbytes + hv0.nbytes, 0]
+        sim.restore_state()
+        eng.upload_xv_stage(hx0, hv0)
 
         def e2e_step():
-            # the previous result is this step's input (the host owns the state; the owned set is that of the
-            # dump): device -> host must be complete before host -> device starts, so only the kernels of the
-            # step and the packing overlap the copies here
-            sim.dump_wait()
-            d = state["d"]
-            sim.upload_xv_async(d["position"], d["velocity"])
+            # every step starts from the saved state (device-side restore, so that the owned set matches the host
+            # arrays), takes its input x, v from pinned host memory and returns its result to the host; the
+            # device -> host copy of step k runs on a copy stream next to the upload and the kernels of step k+1
+            sim.restore_state()
+            eng.upload_xv_commit()
             sim.step(1)
+            eng.upload_xv_stage(hx0, hv0)  # the next step's input, while this step runs
             dump_start()
-            bytes_io[0] = d["position"].nbytes + d["velocity"].nbytes
             bytes_io[1] = sum(state["d"][k].nbytes for k in ("position", "velocity", "material", "orig_id"))
 
         def e2e_finish():
             sim.dump_wait()
-        api = ("ShardedSim.upload_xv_async + ShardedSim.step + ShardedSim.dump_local_async / dump_wait "
+        api = ("ShardedSim.restore_state + Engine.upload_xv_stage / _commit + step + dump_local_async / dump_wait "
                "(per rank; bytes summed over ranks)")
     e2e_step()
     e2e_finish()
@@ -562,7 +587,7 @@ def run_gpu(args):
             except Exception as e:                  # never lose the main line over a side measurement
                 also[key] = {"error": str(e)[:200]}
         line["config"]["also"] = also
-    print(json.dumps(line), flush=True)
+    emit(line)
     if sim is not None:
         import torch.distributed as dist
         sim.close()
@@ -599,12 +624,14 @@ def main():
         args.warmup = 3
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":
+        claim_stdout()
         return run_reference_impl(args)
     if world == 1 and args.gpus > 1:
         # launched without torchrun: re-launch ourselves one rank per GPU
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
                "--master-addr", "127.0.0.1", "--master-port", "29531", os.path.abspath(__file__)] + sys.argv[1:]
         raise SystemExit(subprocess.call(cmd))
+    claim_stdout()
     run_gpu(args)
 
 

@@ -201,6 +201,10 @@ int tisph_upload_xv(tisph_ctx *ctx, const float *pos, const float *vel);
  * velocity [n][dim] f32, material [n] i32, colour [n][3] (gen-2) / [n] (gen-1) i32, plus the original ids
  * [n] i32; any destination may be NULL. */
 int tisph_upload_xv_async(tisph_ctx *ctx, const float *pos, const float *vel);
+/* tisph_upload_xv_async in its two halves: _stage starts the host->device copy of n particles and may be
+ * called while a step is still running; _commit (between steps) makes them the x, v of the n owned particles. */
+int tisph_upload_xv_stage(tisph_ctx *ctx, const float *pos, const float *vel, int32_t n);
+int tisph_upload_xv_commit(tisph_ctx *ctx);
 int tisph_dump_async(tisph_ctx *ctx, float *pos, float *vel, int32_t *material, int32_t *color, int32_t *orig_id);
 int tisph_dump_wait(tisph_ctx *ctx);
 /* Zero-copy hand-off (ggui scene.particles(ps.x), torch, cupy): device pointer of the packed

@@ -67,6 +67,8 @@ SYMBOLS = {
     "tisph_download": (C.c_int, [_vp, _i32, _vp, C.c_size_t]),
     "tisph_upload_xv": (C.c_int, [_vp, _vp, _vp]),
     "tisph_upload_xv_async": (C.c_int, [_vp, _vp, _vp]),
+    "tisph_upload_xv_stage": (C.c_int, [_vp, _vp, _vp, _i32]),
+    "tisph_upload_xv_commit": (C.c_int, [_vp]),
     "tisph_dump_async": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "tisph_dump_wait": (C.c_int, [_vp]),
     "tisph_device_ptr": (C.c_int, [_vp, _i32, C.POINTER(_vp), _ip]),

@@ -85,6 +85,7 @@ struct tisph_ctx {
     cudaEvent_t ev_in_done = nullptr, ev_in_free = nullptr, ev_out_ready = nullptr, ev_out_done = nullptr;
     void *ain = nullptr, *aout = nullptr;
     bool out_pending = false;
+    int in_staged = -1;                // particles staged by tisph_upload_xv_stage, -1 = none
     float4 *snapP = nullptr, *snapV = nullptr, *snapQ = nullptr;   // tisph_state_save
     int snap_n = -1;
     int diagnostics = 0;
@@ -821,26 +822,52 @@ static int async_setup(tisph_ctx* c) {
     return TISPH_OK;
 }
 
-int tisph_upload_xv_async(tisph_ctx* c, const float* pos, const float* vel) {
+// host -> device half of an asynchronous upload: may be issued while a step is still running
+int tisph_upload_xv_stage(tisph_ctx* c, const float* pos, const float* vel, int32_t n) {
     CHECK_CTX(c);
-    if (!pos || !vel) return fail(TISPH_ERR_INVALID, "null argument");
-    if (c->phase != 0 || c->uphase != 0 || c->appended) return fail(TISPH_ERR_INVALID, "cannot upload in the middle of a step");
-    { int rc = ensure_range(c); if (rc) return rc; }
+    if (!pos || !vel || n < 0 || n > c->cap) return fail(TISPH_ERR_INVALID, "bad argument");
     { int rc = async_setup(c); if (rc) return rc; }
-    int n = c->o_hi - c->o_lo, dim = c->cfg.dim;
-    if (n == 0) return TISPH_OK;
+    const int dim = c->cfg.dim;
     float* d_pos = (float*)c->ain;
     float* d_vel = d_pos + (size_t)n * dim;
     CU(cudaStreamWaitEvent(c->copy_in, c->ev_in_free, 0));          // the previous upload's kernel has read the block
-    CU(cudaMemcpyAsync(d_pos, pos, (size_t)n * dim * 4, cudaMemcpyHostToDevice, c->copy_in));
-    CU(cudaMemcpyAsync(d_vel, vel, (size_t)n * dim * 4, cudaMemcpyHostToDevice, c->copy_in));
+    if (n > 0) {
+        CU(cudaMemcpyAsync(d_pos, pos, (size_t)n * dim * 4, cudaMemcpyHostToDevice, c->copy_in));
+        CU(cudaMemcpyAsync(d_vel, vel, (size_t)n * dim * 4, cudaMemcpyHostToDevice, c->copy_in));
+    }
     CU(cudaEventRecord(c->ev_in_done, c->copy_in));
+    c->in_staged = n;
+    return TISPH_OK;
+}
+
+// device half: the staged x, v replace those of the (owned) particles, in their current order
+int tisph_upload_xv_commit(tisph_ctx* c) {
+    CHECK_CTX(c);
+    if (c->in_staged < 0) return fail(TISPH_ERR_INVALID, "nothing staged (tisph_upload_xv_stage)");
+    if (c->phase != 0 || c->uphase != 0 || c->appended) return fail(TISPH_ERR_INVALID, "cannot upload in the middle of a step");
+    { int rc = ensure_range(c); if (rc) return rc; }
+    const int n = c->o_hi - c->o_lo, dim = c->cfg.dim;
+    if (n != c->in_staged)
+        return fail(TISPH_ERR_INVALID, "%d particles were staged, the context owns %d", c->in_staged, n);
+    c->in_staged = -1;
+    if (n == 0) return TISPH_OK;
+    float* d_pos = (float*)c->ain;
+    float* d_vel = d_pos + (size_t)n * dim;
     CU(cudaStreamWaitEvent(c->stream, c->ev_in_done, 0));
     k_upload_xv<<<nblocks(n, 256), 256, 0, c->stream>>>(n, dim, d_pos, d_vel, c->P[c->cur] + c->o_lo, c->V[c->cur] + c->o_lo);
     c->launches += 1;
     CU(cudaGetLastError());
     CU(cudaEventRecord(c->ev_in_free, c->stream));
     return TISPH_OK;
+}
+
+int tisph_upload_xv_async(tisph_ctx* c, const float* pos, const float* vel) {
+    CHECK_CTX(c);
+    if (!pos || !vel) return fail(TISPH_ERR_INVALID, "null argument");
+    if (c->phase != 0 || c->uphase != 0 || c->appended) return fail(TISPH_ERR_INVALID, "cannot upload in the middle of a step");
+    { int rc = ensure_range(c); if (rc) return rc; }
+    int rc = tisph_upload_xv_stage(c, pos, vel, c->o_hi - c->o_lo);
+    return rc ? rc : tisph_upload_xv_commit(c);
 }
 
 int tisph_dump_wait(tisph_ctx* c) {

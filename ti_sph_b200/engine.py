@@ -92,6 +92,16 @@ class Engine:
         assert pos.size == n * self.dim and vel.size == n * self.dim
         check(self._lib.tisph_upload_xv_async(self._ctx, _ptr(pos), _ptr(vel)))
 
+    def upload_xv_stage(self, pos, vel):
+        """first half of upload_xv_async: start the host->device copy; allowed while a step is running"""
+        assert pos.dtype == np.float32 and vel.dtype == np.float32 and pos.flags.c_contiguous and vel.flags.c_contiguous
+        assert pos.size == vel.size and pos.size % self.dim == 0
+        check(self._lib.tisph_upload_xv_stage(self._ctx, _ptr(pos), _ptr(vel), pos.size // self.dim))
+
+    def upload_xv_commit(self):
+        """second half: between steps, the staged arrays become x, v of the owned particles"""
+        check(self._lib.tisph_upload_xv_commit(self._ctx))
+
     def dump_async(self, position=None, velocity=None, material=None, color=None, orig_id=None):
         """start filling the given preallocated host arrays (any subset) with the current state; they are
         complete after dump_wait()"""
