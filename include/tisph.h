@@ -209,7 +209,9 @@ int tisph_dump_async(tisph_ctx *ctx, float *pos, float *vel, int32_t *material, 
 int tisph_dump_wait(tisph_ctx *ctx);
 /* Zero-copy hand-off (ggui scene.particles(ps.x), torch, cupy): device pointer of the packed
  * float4 arrays {x,y,z,mass} (TISPH_F_X) / {vx,vy,vz,volume} (TISPH_F_V) / {ax,ay,az,0}
- * (TISPH_F_D_VELOCITY); valid until the next step. */
+ * (TISPH_F_D_VELOCITY); valid until the next step.  This call does NOT synchronise: tisph_step is
+ * asynchronous on the context's own stream, so a consumer on another stream calls tisph_sync first
+ * (the Python field views do) or shares its stream through tisph_set_stream. */
 int tisph_device_ptr(tisph_ctx *ctx, int32_t field, void **ptr, int32_t *stride_bytes);
 
 int tisph_set_param(tisph_ctx *ctx, int32_t param, double value);
