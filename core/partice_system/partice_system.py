@@ -48,6 +48,11 @@ class ParticleSystem:
                           ("particle_neighbors", K.F_NEIGHBORS), ("particle_neighbors_num", K.F_NEIGHBOR_COUNT),
                           ("grid_particles_num", K.F_GRID_PARTICLES_NUM)):
             setattr(self, name, FieldView(self, fid, name))
+        self._overrides = {}         # field name -> library field, while a step is driven kernel by kernel
+        self._kernel_stage = 0       # ... and how far that step got (core/sph/sph_base.py)
+
+    def _field_override(self, name, field):
+        return self._overrides.get(name, field)
 
     # ---- particles -------------------------------------------------------------------------
     def add_particles(self, num, particle_position, particle_velocity, particle_density,
@@ -75,6 +80,8 @@ class ParticleSystem:
     # ---- per step ----------------------------------------------------------------------------
     def init(self):
         """clear the grid and the neighbour table, rebuild both (partice_system.py:211-215)"""
+        self._overrides.clear()
+        self._kernel_stage = 0
         self.engine.stage(K.STAGE_UPDATE)
 
     def pos_to_index(self, pos):

@@ -152,8 +152,13 @@ typedef enum tisph_param {
     TISPH_P_VISCOSITY = 16,   /* SPHBase(V2).viscosity, sph_basev2.py:12 (the kernels' coefficients follow) */
     TISPH_P_DENSITY0 = 17,    /* SPHBase(V2).density_0, sph_basev2.py:13 */
     TISPH_P_GRAVITY_X = 18, TISPH_P_GRAVITY_Y = 19, TISPH_P_GRAVITY_Z = 20,   /* SPHBaseV2.g, sph_basev2.py:16 */
-    TISPH_P_MAX_SPEED = 21    /* read-only: max |v| over the fluid particles this context owns (synchronises);
+    TISPH_P_MAX_SPEED = 21,   /* read-only: max |v| over the fluid particles this context owns (synchronises);
                                  a sharded run max-reduces it over the ranks to agree on a CFL step */
+    TISPH_P_SKIP_DISCARDED_SUM = 22 /* opt-in, default 0.  density_mode 0 reproduces wcsphv2.py:32-34, where the neighbour
+                                 sum is accumulated and then overwritten; by default the sum is computed all the same
+                                 (TISPH_F_DENSITY_SUM, TISPH_F_NEIGHBOR_COUNT).  1: a caller that reads neither lets the
+                                 density walk build the neighbour lists only (no effect in the other modes, nor while
+                                 TISPH_P_DIAGNOSTICS is on).  Every field of the reference comes out the same. */
 } tisph_param;
 
 const char *tisph_last_error(void);

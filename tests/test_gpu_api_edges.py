@@ -165,3 +165,20 @@ def test_asynchronous_upload_and_dump_match_the_blocking_calls():
     ps_a.engine.sync()                                       # sync() completes a pending dump too
     assert np.array_equal(ids, ps_b.engine.download(K.F_ORIG_ID))
     ps_a.engine.close(); ps_b.engine.close()
+
+
+def test_skipping_the_discarded_sum_changes_no_field_of_the_reference():
+    """TISPH_P_SKIP_DISCARDED_SUM (opt-in): in the reference density mode the neighbour sum is overwritten
+    (wcsphv2.py:32-34), so a density walk that only builds the lists must give bit-identical x, v, density,
+    pressure and d_velocity; in summed mode the switch has no effect"""
+    for mode in ("reference", "summed"):
+        scene = small_scene(end=(0.5, 0.3, 0.9))
+        ora, a = make_pair(scene, density_mode=mode)
+        _, b = make_pair(scene, density_mode=mode)
+        b.set_param(K.P_SKIP_DISCARDED_SUM, 1)
+        a.step(3); b.step(3)
+        for f in (K.F_X, K.F_V, K.F_DENSITY, K.F_PRESSURE, K.F_D_VELOCITY, K.F_ORIG_ID):
+            assert np.array_equal(a.download(f), b.download(f)), (mode, f)
+        same_sum = np.array_equal(a.download(K.F_DENSITY_SUM), b.download(K.F_DENSITY_SUM))
+        assert same_sum == (mode == "summed")
+        a.close(); b.close()

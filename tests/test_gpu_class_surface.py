@@ -167,3 +167,47 @@ def test_zero_copy_view_right_after_step_needs_no_manual_sync():
         x_host = ps.x.to_numpy()
         assert np.array_equal(x_dev.cpu().numpy(), x_host)
     ps.engine.close()
+
+
+@pytest.mark.parametrize("name", ["gen1_cube", "gen1_scene"])
+def test_gen1_kernel_by_kernel_driver_matches_the_reference_vectors(name):
+    """the gen-1 classes driven like tests/golden/make_golden.py:run_gen1 drives the reference's"""
+    from core.partice_system.partice_system import ParticleSystem
+    from core.partice_system.partice_systemv2 import ParticleSystemV2
+    from core.sph.wcsph import WCSPH
+    from oracle.oracle import Gen1Oracle
+    z = np.load(os.path.join(GOLD, name + ".npz"))
+    case = json.loads(str(z["case_json"]))
+    if case["kind"] == "v1":
+        ps = ParticleSystem(tuple(case["res"]))
+        ps.add_cube(**case["cube"])
+    else:
+        ps = ParticleSystemV2(tuple(case["res"]), case["scene"])
+        ps.add_fluid_and_rigid()
+    solver = WCSPH(ps)
+    g = lambda k: z[f"s0.{k}"]
+    ps.init()
+    assert np.array_equal(ps.particle_neighbors.to_numpy(), g("init.particle_neighbors"))
+    assert np.array_equal(ps.particle_neighbors_num.to_numpy(), g("init.particle_neighbors_num"))
+    solver.compute_volume_of_boundary_particle()
+    solver.compute_densities()
+    assert rel_err(ps.density.to_numpy(), g("density.density"), floor=1.0) < RTOL
+    ora = Gen1Oracle(tuple(case["res"]))
+    ora.material = z["init.material"]
+    mags = ora.force_magnitudes(z["init.x"], z["init.v"], g("density.density"), g("pressure.density"),
+                                g("pressure.pressure"), g("init.particle_neighbors"), g("init.particle_neighbors_num"))
+    solver.compute_non_pressure_force()
+    assert accel_err(solver.d_velocity.to_numpy(), g("nonpressure.d_velocity"), mags["mag_nonpressure"]) < RTOL
+    assert np.array_equal(ps.x.to_numpy(), z["init.x"])                      # not advected yet
+    solver.compute_pressure_force()
+    assert rel_err(ps.density.to_numpy(), g("pressure.density")) < RTOL
+    mag = mags["mag_nonpressure"].astype(np.float64) + mags["mag_pressure"]
+    assert accel_err(solver.d_velocity.to_numpy(), g("pressure.d_velocity"), mag,
+                     mags["mag_pressure_floor"] + RTOL * mags["mag_pressure"]) < RTOL
+    solver.advert()
+    solver.enforce_boundary()
+    assert rel_err(ps.x.to_numpy(), g("end.x"), floor=0.2) < RTOL
+    # the unmodified step() continues from here like a fresh system that took one fused step
+    solver.step()
+    assert ps._kernel_stage == 0
+    ps.engine.close()

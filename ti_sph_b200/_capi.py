@@ -44,7 +44,7 @@ STAGE_UPDATE, STAGE_DENSITY, STAGE_FORCE_ADVECT, STAGE_UPDATE_BIN, STAGE_UPDATE_
 P_DT, P_DENSITY_MODE, P_VOLUME_MODE, P_DIAGNOSTICS, P_KERNEL_VARIANT, P_ID_BASE, P_HAS_BOUNDARY, \
     P_STAT_ITEMS, P_STAT_FALLBACK_DENSITY, P_STAT_FALLBACK_FORCE, P_CFL, P_STAT_CHECK_FAILURES, \
     P_SPLIT_WALLS, P_PHASE, P_STIFFNESS, P_EXPONENT, P_VISCOSITY, P_DENSITY0, P_GRAVITY_X, P_GRAVITY_Y, \
-    P_GRAVITY_Z, P_MAX_SPEED = range(22)
+    P_GRAVITY_Z, P_MAX_SPEED, P_SKIP_DISCARDED_SUM = range(23)
 ABI_VERSION = 2
 
 ERR_NO_DEVICE = -5

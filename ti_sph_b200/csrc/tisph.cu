@@ -57,6 +57,7 @@ struct tisph_ctx {
     int cur = 0;         // which copy holds the authoritative particle records
     int phase = 0;       // 0: between steps, 1: after UPDATE, 2: after DENSITY
     int uphase = 0;      // inside UPDATE: 1 after UPDATE_BIN, 2 after UPDATE_SCAN
+    bool skip_sum = false;          // TISPH_P_SKIP_DISCARDED_SUM
     bool walls_pending = false;     // a split force stage ran: TISPH_STAGE_WALLS is due
     int* new_index = nullptr;       // paritcle_index_temp (diagnostics only)
     bool have_sorted = false;
@@ -133,7 +134,7 @@ static void fill_params(tisph_ctx* c);
 static void fill_physics(tisph_ctx* c) {
     SimParams keep = c->sp;
     fill_params(c);
-    c->sp.n = keep.n; c->sp.dt = keep.dt; c->sp.walls = keep.walls;
+    c->sp.n = keep.n; c->sp.dt = keep.dt; c->sp.walls = keep.walls; c->sp.lists_only = keep.lists_only;
     c->sp.own_key_lo = keep.own_key_lo; c->sp.own_key_hi = keep.own_key_hi;
     c->sp.walk_key_lo = keep.walk_key_lo; c->sp.walk_key_hi = keep.walk_key_hi;
     c->sp.ghost_walk = keep.ghost_walk;
@@ -163,6 +164,7 @@ static void fill_params(tisph_ctx* c) {
     s.int_exponent = (e >= 1.0f && e <= 64.0f && e == floorf(e)) ? (int)e : 0;
     s.one = 1.0f;
     s.walls = 1;
+    s.lists_only = 0;
     s.own_key_lo = 0; s.own_key_hi = 0x7fffffff;
     s.walk_key_lo = 0; s.walk_key_hi = 0x7fffffff;
     s.ghost_walk = 1;
@@ -336,6 +338,8 @@ static int run_density(tisph_ctx* c) {
         c->phase = 2;
         return TISPH_OK;
     }
+    // TISPH_P_SKIP_DISCARDED_SUM only applies where the sum really is discarded
+    c->sp.lists_only = (c->skip_sum && c->sp.density_mode == 0 && c->sp.volume_mode == 0 && !c->diagnostics) ? 1 : 0;
     // ghost cells: their density is needed by the force walk, but in the reference modes it is mass * W(0)
     c->sp.ghost_walk = (c->sp.density_mode == 0 && c->sp.volume_mode == 0) ? 0 : 1;
     auto kd = c->sp.volume_mode == 1 ? k_density_list<true> : k_density_list<false>;
@@ -938,6 +942,7 @@ int tisph_set_param(tisph_ctx* c, int32_t param, double value) {
         case TISPH_P_SPLIT_WALLS:
             if (c->phase == 0 && c->walls_pending) return fail(TISPH_ERR_INVALID, "TISPH_STAGE_WALLS is due");
             c->sp.walls = value != 0.0 ? 0 : 1; return TISPH_OK;
+        case TISPH_P_SKIP_DISCARDED_SUM: c->skip_sum = value != 0.0; return TISPH_OK;
         case TISPH_P_STIFFNESS: c->cfg.stiffness = c->sp.stiffness = (float)value; return TISPH_OK;
         case TISPH_P_EXPONENT: c->cfg.exponent = (float)value; fill_physics(c); return TISPH_OK;
         case TISPH_P_VISCOSITY:      // wcsphv2.py:69 (2 nu h c_s) ; sph_base.py:81 (2 (dim+2) nu)
@@ -989,6 +994,7 @@ int tisph_get_param(tisph_ctx* c, int32_t param, double* value) {
             return TISPH_OK;
         }
         case TISPH_P_SPLIT_WALLS: *value = c->sp.walls ? 0 : 1; return TISPH_OK;
+        case TISPH_P_SKIP_DISCARDED_SUM: *value = c->skip_sum; return TISPH_OK;
         case TISPH_P_PHASE: *value = c->phase + 10 * c->uphase; return TISPH_OK;
         case TISPH_P_STIFFNESS: *value = c->cfg.stiffness; return TISPH_OK;
         case TISPH_P_EXPONENT: *value = c->cfg.exponent; return TISPH_OK;

@@ -43,6 +43,7 @@ struct SimParams {
     float g1_visc_c, g1_mass, g1_press_c, m_V0;
     int density_mode, volume_mode;
     int int_exponent;      // exponent if it is a small positive integer, else 0
+    int lists_only;        // 1: the density walk builds the neighbour lists but skips the (discarded) kernel sum
     int walls;             // 1: the force stage applies enforce_boundary itself (default), 0: TISPH_STAGE_WALLS does
     float one;             // 1.0f the compiler cannot see (tisph_lists.cuh: uncontracted packed sums)
     // slab sharding (tisph_shard.cuh): cell-key ranges [lo, hi).  Unsharded: [0, INT_MAX).

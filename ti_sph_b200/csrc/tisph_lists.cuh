@@ -267,7 +267,9 @@ k_density_list(SimParams sp, const int* __restrict__ cell_end, const int2* __res
             const uint32_t nmax = __reduce_max_sync(0xffffffffu, n2);
             for (uint32_t k = 2u * nA; k < nmax; k += 2u) sts_u8(sL + offA + k, M_DUMMY);
             for (uint32_t k = 2u * nB; k < nmax; k += 2u) sts_u8(sL + offB + k, M_DUMMY + 1);
-            for (uint32_t k2 = 0; k2 < nmax; k2 += 2u) {
+            // (sp.lists_only: the caller declared that it reads neither the density sum nor the neighbour
+            //  count and the density mode discards the sum -- then only the lists are needed)
+            for (uint32_t k2 = 0; k2 < (sp.lists_only ? 0u : nmax); k2 += 2u) {
                 const uint32_t w = lds_u16(sL + k2);
                 const uint32_t m1 = w & 0xffu, m2 = w >> 8;
                 TISPH_CHECK((m1 & 1u) == c1 && (m2 & 1u) == 1u - c1 && k2 < 2u * LCAP2 + 4u);
