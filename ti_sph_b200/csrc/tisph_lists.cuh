@@ -34,6 +34,8 @@
 // {x,y} {z,psi} {vx,vy} {vz,rho} p/rho^2 from 8-byte planes and evaluates cohesion, artificial
 // viscosity and pressure for two neighbours at a time, branch-free; then advect + walls.
 #pragma once
+#include <cuda_fp16.h>
+
 #include "tisph_walk.cuh"
 
 namespace tisph {
@@ -87,8 +89,19 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
 
 // =======================================================================================
 // Walk 1: boundary volume, density summation, clamp, Tait EOS; builds the neighbour lists
-//   FXY[8k+j] = {-xa,-xb,-ya,-yb}, FZ[8k+j] = {-za,-zb}: a = slot 16k+j (row 2k), b = slot 16k+8+j (row 2k+1)
-//   GXY[s] = {x,y} of slot s (the drain's gathers; z comes from FZ)      GM[s] = material (Akinci volumes only)
+//
+// FILTER tile, half precision.  The filter only has to find a SUPERSET of the neighbours (the drain applies
+// the exact IEEE test), so it runs on binary16 copies of the positions: u = (x - cell centre) / h, rounded
+// to half, |u| <= 1.5 for every candidate.  For a pair within the cutoff the half-precision distance
+// differs from the true one by at most 5.3e-3 (coordinates: 1.2e-4 target + 4.9e-4 candidate + 4.9e-4
+// difference per component, 2 sqrt(3) x that on d2; three roundings of 4.9e-4 in the sum), so accepting
+// d2_half < 1 + 7/1024 = 1.0068 loses nobody and lets ~1 % extra candidates through (they fail the exact
+// test in the drain and evaluate to exact zeros in the force walk).  Two rows (m = 2k, 2k+1: slots 16k+j,
+// 16k+8+j) are the two halves of a half2; the row pairs k = 2kk, 2kk+1 of lane class j are one 24-byte record:
+//   HA[8 kk + j] = {x(2kk), y(2kk), z(2kk), x(2kk+1)}   HB[8 kk + j] = {y(2kk+1), z(2kk+1)}      (half2 each, NEGATED)
+// Half the bytes and half the FMA-pipe time of the f32x2 filter of round 1.
+// DRAIN planes, single precision:  GXY[s] = {x,y}, GZ[s] = z of slot s;  GM[s] = material (Akinci volumes only)
+//
 // A pass runs in two phases with different thread arrangements over the same (target, lane) lists:
 //   FILTER  thread = (lane j = warp index, target = lane id): the 32 threads of a warp test the SAME
 //           candidates against 32 targets, so the tile is read with broadcast loads;
@@ -99,9 +112,26 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
 // =======================================================================================
 constexpr int LIST_T = LSTRIDE / 4;              // 25 words
 constexpr int LIST_J = PASS_T * LIST_T + 4;      // 804 words: = 4 (mod 32)
-constexpr size_t DL_SMEM = (size_t)LT_ROWS * 8 * (sizeof(float4) + sizeof(float2)) + (size_t)LT_SLOTS * sizeof(float2) +
+constexpr float HCUT = 1.0f + 7.0f / 1024.0f;    // filter threshold on the half-precision d2 / h^2 (see above)
+constexpr size_t DL_SMEM = (size_t)(LT_ROWS / 2) * 8 * (sizeof(uint4) + sizeof(uint2)) + (size_t)LT_SLOTS * (sizeof(float2) + sizeof(float)) +
                            (size_t)GL * LIST_J * 4 + (size_t)NB_THREADS * 2;
 constexpr size_t DL_SMEM_AKINCI = DL_SMEM + (size_t)LT_SLOTS * sizeof(int);
+
+__device__ __forceinline__ uint32_t h2_bits(__half2 v) { return *reinterpret_cast<uint32_t*>(&v); }
+__device__ __forceinline__ __half2 bits_h2(uint32_t v) { return *reinterpret_cast<__half2*>(&v); }
+
+// one row pair of the filter: s = |u_i - u_j|^2 - HCUT for the two rows (negative = survivor), then the
+// predicated pushes of the row bytes m, m+1 to the two pending streams
+__device__ __forceinline__ void filter_rows(__half2 xi, __half2 yi, __half2 zi, __half2 ncut, uint32_t nx, uint32_t ny,
+                                            uint32_t nz, uint32_t m, uint32_t& pA, uint32_t& pB) {
+    const __half2 dx = __hadd2(xi, bits_h2(nx)), dy = __hadd2(yi, bits_h2(ny)), dz = __hadd2(zi, bits_h2(nz));
+    const __half2 s = __hfma2(dz, dz, __hfma2(dy, dy, __hfma2(dx, dx, ncut)));
+    asm volatile("{\n\t.reg .pred p, q;\n\t.reg .b32 z;\n\tmov.b32 z, 0;\n\t"
+                 "setp.lt.f16x2 p|q, %2, z;\n\t"
+                 "@p st.shared.u8 [%0], %3;\n\t@p add.u32 %0, %0, 2;\n\t"
+                 "@q st.shared.u8 [%1], %4;\n\t@q add.u32 %1, %1, 2;\n\t}"
+                 : "+r"(pA), "+r"(pB) : "r"(h2_bits(s)), "r"(m), "r"(m + 1u) : "memory");
+}
 
 template <bool AKINCI>
 __global__ void __launch_bounds__(NB_THREADS, 3)
@@ -112,10 +142,11 @@ k_density_list(SimParams sp, const int* __restrict__ cell_end, const int2* __res
                uint32_t* __restrict__ Lg, int* __restrict__ item_row, unsigned char* __restrict__ flags,
                int* __restrict__ fb_d, int* __restrict__ fb_f) {
     extern __shared__ float4 dyn_smem[];
-    float4* FXY = dyn_smem;
-    float2* FZ = reinterpret_cast<float2*>(FXY + LT_ROWS * 8);
-    float2* GXY = FZ + LT_ROWS * 8;
-    unsigned char* L = reinterpret_cast<unsigned char*>(GXY + LT_SLOTS);
+    uint4* HA = reinterpret_cast<uint4*>(dyn_smem);
+    uint2* HB = reinterpret_cast<uint2*>(HA + (LT_ROWS / 2) * 8);
+    float2* GXY = reinterpret_cast<float2*>(HB + (LT_ROWS / 2) * 8);
+    float* GZ = reinterpret_cast<float*>(GXY + LT_SLOTS);
+    unsigned char* L = reinterpret_cast<unsigned char*>(GZ + LT_SLOTS);
     unsigned short* LC = reinterpret_cast<unsigned short*>(L + GL * LIST_J * 4);     // entries per stream: nA | nB << 8
     int* GM = reinterpret_cast<int*>(LC + NB_THREADS);
     __shared__ CellRanges R;
@@ -124,10 +155,10 @@ k_density_list(SimParams sp, const int* __restrict__ cell_end, const int2* __res
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n_items = ctr->n_items;
-    const float cut_wide = sp.d2_cut * 1.000001f;          // superset filter; the drain applies the exact test
     const float2 one2 = make_float2(sp.one, sp.one);       // see the drain: keeps ptxas from contracting the exact sum
+    const __half2 ncut = __float2half2_rn(-HCUT);
     // ---- filter arrangement: lane jF = warp, target tF = lane
-    const uint32_t fFXY = smem_u32(FXY) + 16u * warp, fFZ = smem_u32(FZ) + 8u * warp;
+    const uint32_t fHA = smem_u32(HA) + 16u * warp, fHB = smem_u32(HB) + 8u * warp;
     const uint32_t fL = smem_u32(L) + 4u * (LIST_J * warp + LIST_T * lane);
     // a row-2k candidate goes to byte 2n + offA of the list, a row-2k+1 candidate to byte 2n + offB: the FIRST
     // entry of every byte pair has the parity of the target's drain group (target & 1)
@@ -135,14 +166,11 @@ k_density_list(SimParams sp, const int* __restrict__ cell_end, const int2* __res
     // ---- drain arrangement: target tid / 8, lane j = tid % 8
     const int j = tid & (GL - 1), tD = tid >> 3;
     const uint32_t c1 = tD & 1u;                           // parity of my group: which stream I consume first
-    const uint32_t sG = smem_u32(GXY) + 8u * j, sGM = smem_u32(GM) + 4u * j;
+    const uint32_t sG = smem_u32(GXY) + 8u * j, sGZ = smem_u32(GZ) + 4u * j, sGM = smem_u32(GM) + 4u * j;
     const uint32_t sL = smem_u32(L) + 4u * (LIST_J * j + LIST_T * tD);
     const uint32_t offA = c1, offB = 1u - c1;
-    // z of row m: FZ word 2 (8 (m >> 1) + j) + (m & 1)  =  byte 32 m + 8 j - 28 (m & 1)
-    const uint32_t zb1 = smem_u32(FZ) + 8u * j - 28u * c1, zb2 = smem_u32(FZ) + 8u * j - 28u * (1u - c1);
-    // the two dummy rows are FAR in every array, for good
-    if (tid < 16) GXY[8 * M_DUMMY + tid] = make_float2(FAR, FAR);
-    if (tid < 8) { FXY[8 * (LT_ROWS - 1) + tid] = make_float4(-FAR, -FAR, -FAR, -FAR); FZ[8 * (LT_ROWS - 1) + tid] = make_float2(-FAR, -FAR); }
+    // the two dummy rows are FAR in every array, for good (half: |u| = 1000 makes d2 overflow to +inf)
+    if (tid < 16) { GXY[8 * M_DUMMY + tid] = make_float2(FAR, FAR); GZ[8 * M_DUMMY + tid] = FAR; }
     if (AKINCI && tid < 16) GM[8 * M_DUMMY + tid] = MAT_FLUID;
 
     ItemFetch nx;
@@ -171,26 +199,37 @@ k_density_list(SimParams sp, const int* __restrict__ cell_end, const int2* __res
         const int walk_total = (own || sp.ghost_walk) ? G.total : 0;
         // ---- stage the tile: rows of 16 candidates, padded with FAR to a whole filter chunk -------------
         const int nrow2 = ((walk_total + 15) / 16 + FCHUNK - 1) / FCHUNK * FCHUNK;      // row pairs (k) staged
+        // centre of the target cell: origin of the half-precision coordinates
+        const float ccx = ((float)(G.c / (sp.gz * sp.gy)) + 0.5f) * sp.h, ccy = ((float)((G.c / sp.gz) % sp.gy) + 0.5f) * sp.h,
+                    ccz = ((float)(G.c % sp.gz) + 0.5f) * sp.h;
         for (int p = tid; p < nrow2 * 8; p += NB_THREADS) {
-            const int sa = 16 * (p >> 3) + (p & 7), sb = sa + 8;      // slots (rows 2k and 2k+1, lane p & 7)
+            const int k = p >> 3, jj = p & 7;
+            const int sa = 16 * k + jj, sb = sa + 8;                  // slots (rows 2k and 2k+1, lane class jj)
             const int ea = slot_to_cand(sa), eb = slot_to_cand(sb);
             float4 a = make_float4(FAR, FAR, FAR, 0.f), b = a;
+            float3 ua = make_float3(-1000.f, -1000.f, -1000.f), ub = ua;       // padding: never within the cutoff
             int ma = MAT_FLUID, mb = MAT_FLUID;
             if (ea < walk_total) {
                 const int g = tile_to_global(R, ea);
                 a = P[g];
+                ua = make_float3((a.x - ccx) * sp.inv_h, (a.y - ccy) * sp.inv_h, (a.z - ccz) * sp.inv_h);
                 if (AKINCI) ma = __float_as_int(Q[g].z);
             }
             if (eb < walk_total) {
                 const int g = tile_to_global(R, eb);
                 b = P[g];
+                ub = make_float3((b.x - ccx) * sp.inv_h, (b.y - ccy) * sp.inv_h, (b.z - ccz) * sp.inv_h);
                 if (AKINCI) mb = __float_as_int(Q[g].z);
             }
             TISPH_CHECK(sb < LT_SLOTS && p < LT_ROWS * 8);
-            FXY[p] = make_float4(-a.x, -b.x, -a.y, -b.y);
-            FZ[p] = make_float2(-a.z, -b.z);
-            GXY[sa] = make_float2(a.x, a.y);
-            GXY[sb] = make_float2(b.x, b.y);
+            const uint32_t hx = h2_bits(__floats2half2_rn(-ua.x, -ub.x)), hy = h2_bits(__floats2half2_rn(-ua.y, -ub.y)),
+                           hz = h2_bits(__floats2half2_rn(-ua.z, -ub.z));
+            uint32_t* ha = reinterpret_cast<uint32_t*>(HA + 8 * (k >> 1) + jj);
+            uint32_t* hb = reinterpret_cast<uint32_t*>(HB + 8 * (k >> 1) + jj);
+            if ((k & 1) == 0) { ha[0] = hx; ha[1] = hy; ha[2] = hz; }
+            else { ha[3] = hx; hb[0] = hy; hb[1] = hz; }
+            GXY[sa] = make_float2(a.x, a.y); GZ[sa] = a.z;
+            GXY[sb] = make_float2(b.x, b.y); GZ[sb] = b.z;
             if (AKINCI) { GM[sa] = ma; GM[sb] = mb; }
         }
         __syncthreads();
@@ -202,31 +241,30 @@ k_density_list(SimParams sp, const int* __restrict__ cell_end, const int2* __res
             int ovf = 0;
             {
                 const int tf = pass * PASS_T + lane;
-                const float4 pf = tf < G.nT ? P[G.i0 + tf] : make_float4(-FAR, -FAR, -FAR, 0.f);
-                const float2 xi2 = make_float2(pf.x, pf.x), yi2 = make_float2(pf.y, pf.y), zi2 = make_float2(pf.z, pf.z);
+                float3 uf = make_float3(1000.f, 1000.f, 1000.f);       // idle lane: far from everything
+                if (tf < G.nT) {
+                    const float4 pf = P[G.i0 + tf];
+                    uf = make_float3((pf.x - ccx) * sp.inv_h, (pf.y - ccy) * sp.inv_h, (pf.z - ccz) * sp.inv_h);
+                }
+                const __half2 xi = __float2half2_rn(uf.x), yi = __float2half2_rn(uf.y), zi = __float2half2_rn(uf.z);
                 uint32_t pA = fA, pB = fB;                     // next free byte of the two pending streams
                 for (int k0 = 0; k0 < nrow2; k0 += FCHUNK) {
-                    // loads are issued four row pairs ahead of their use
+                    // FCHUNK row pairs = FCHUNK / 2 records of 24 bytes; all loads first
+                    uint4 ra[FCHUNK / 2];
+                    uint2 rb[FCHUNK / 2];
 #pragma unroll
-                    for (int b4 = 0; b4 < FCHUNK; b4 += 4) {
-                        float4 c[4];
-                        float2 cz[4];
+                    for (int u = 0; u < FCHUNK / 2; ++u) {
+                        const uint32_t kk = (uint32_t)(k0 >> 1) + u;
+                        asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(ra[u].x), "=r"(ra[u].y), "=r"(ra[u].z), "=r"(ra[u].w)
+                                     : "r"(fHA + 128u * kk) : "memory");
+                        asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(rb[u].x), "=r"(rb[u].y) : "r"(fHB + 64u * kk) : "memory");
+                    }
 #pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            c[u] = lds_f32x4(fFXY + 128u * (k0 + b4 + u));
-                            cz[u] = lds_f32x2(fFZ + 64u * (k0 + b4 + u));
-                        }
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            const float2 dx = __fadd2_rn(xi2, make_float2(c[u].x, c[u].y));
-                            const float2 dy = __fadd2_rn(yi2, make_float2(c[u].z, c[u].w));
-                            const float2 dz = __fadd2_rn(zi2, cz[u]);
-                            const float2 s = __ffma2_rn(dz, dz, __ffma2_rn(dy, dy, __fmul2_rn(dx, dx)));
-                            const uint32_t m = 2u * (k0 + b4 + u);
-                            TISPH_CHECK(pA - fL < 2u * LCAP2 + 2u && pB - fL < 2u * LCAP2 + 2u);
-                            if (s.x < cut_wide) { sts_u8(pA, m); pA += 2u; }
-                            if (s.y < cut_wide) { sts_u8(pB, m + 1u); pB += 2u; }
-                        }
+                    for (int u = 0; u < FCHUNK / 2; ++u) {
+                        const uint32_t m = 2u * (k0 + 2 * u);
+                        TISPH_CHECK(pA - fL < 2u * LCAP2 + 2u && pB - fL < 2u * LCAP2 + 2u);
+                        filter_rows(xi, yi, zi, ncut, ra[u].x, ra[u].y, ra[u].z, m, pA, pB);
+                        filter_rows(xi, yi, zi, ncut, ra[u].w, rb[u].x, rb[u].y, m + 2u, pA, pB);
                     }
                     // a stream that could overflow with the next chunk: the whole item goes to the fallback kernels
                     if (max(pA - fA, pB - fB) > 2u * (LCAP2 - FCHUNK)) { ovf = 1; break; }
@@ -261,25 +299,39 @@ k_density_list(SimParams sp, const int* __restrict__ cell_end, const int2* __res
                 TISPH_CHECK(lo < ((ms & 1u) ? nB : nA) && lds_u8(sb + 2u * lo) == ms);
                 sts_u8(sb + 2u * lo, M_DUMMY + (ms & 1u));
             }
-            // pad both streams with their dummy row to the longest list of the warp, then one (first, second)
-            // pair of entries per iteration, branch-free
-            const uint32_t n2 = (2u * max(nA, nB) + 2u) & ~3u;
+            // The two streams are consumed in lockstep (here and in the force walk), so the longer one sets the
+            // number of iterations: level them by moving tail entries across (the parity only matters for the
+            // banks: an entry in the "wrong" stream costs its gathers a two-way conflict; ~1 in 10 moves).
+            {
+                const bool a_long = nA > nB;
+                const uint32_t ns = a_long ? nA : nB, nd = a_long ? nB : nA;
+                const uint32_t src = sL + (a_long ? offA : offB), dst = sL + (a_long ? offB : offA);
+                const uint32_t mv = min(8u, (ns - nd) >> 1);                // (loads first: their latencies overlap)
+                uint32_t e[8];
+#pragma unroll
+                for (uint32_t u = 0; u < 8u; ++u) if (u < mv) e[u] = lds_u8(src + 2u * (ns - 1u - u));
+#pragma unroll
+                for (uint32_t u = 0; u < 8u; ++u) if (u < mv) sts_u8(dst + 2u * (nd + u), e[u]);
+                nA = a_long ? ns - mv : nd + mv;
+                nB = a_long ? nd + mv : ns - mv;
+            }
+            // pad both streams with their dummy row to the longest list of the warp (whole words), then one
+            // (first, second) pair of entries per iteration, branch-free
+            const uint32_t n2 = (2u * max(nA, nB) + 2u) & ~3u;                  // 2 x pairs I hand to the force walk
             const uint32_t nmax = __reduce_max_sync(0xffffffffu, n2);
             for (uint32_t k = 2u * nA; k < nmax; k += 2u) sts_u8(sL + offA + k, M_DUMMY);
             for (uint32_t k = 2u * nB; k < nmax; k += 2u) sts_u8(sL + offB + k, M_DUMMY + 1);
-            // (sp.lists_only: the caller declared that it reads neither the density sum nor the neighbour
-            //  count and the density mode discards the sum -- then only the lists are needed)
             for (uint32_t k2 = 0; k2 < (sp.lists_only ? 0u : nmax); k2 += 2u) {
                 const uint32_t w = lds_u16(sL + k2);
                 const uint32_t m1 = w & 0xffu, m2 = w >> 8;
-                TISPH_CHECK((m1 & 1u) == c1 && (m2 & 1u) == 1u - c1 && k2 < 2u * LCAP2 + 4u);
+                TISPH_CHECK(k2 < 2u * LCAP2 + 4u && m1 < 256u && m2 < 256u);
                 const float2 xy1 = lds_f32x2(sG + 64u * m1);
-                const float nz1 = lds_f32(zb1 + 32u * m1);
+                const float z1 = lds_f32(sGZ + 32u * m1);
                 const float2 xy2 = lds_f32x2(sG + 64u * m2);
-                const float nz2 = lds_f32(zb2 + 32u * m2);
+                const float z2 = lds_f32(sGZ + 32u * m2);
                 const float2 dx = make_float2(pi.x - xy1.x, pi.x - xy2.x);
                 const float2 dy = make_float2(pi.y - xy1.y, pi.y - xy2.y);
-                const float2 dz = make_float2(pi.z + nz1, pi.z + nz2);
+                const float2 dz = make_float2(pi.z - z1, pi.z - z2);
                 // d2 in the reference's evaluation order with every product rounded (dist2_exact, two at a
                 // time).  ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even with explicit .rn, so the
                 // sums are written as fma(y2, 1, x2) with a run-time 1: exact, and nothing left to contract.
@@ -313,27 +365,7 @@ k_density_list(SimParams sp, const int* __restrict__ cell_end, const int2* __res
             // ---- hand my pairs to the force walk: the warp reserves a count row and the rows of its longest
             //      lane (rows of 32 words), then copies whole words of (first, second, first, second) entries
             if (own) {
-                // The force walk consumes the two streams in lockstep, so the longer one sets its number of
-                // iterations: level them by moving tail entries across (there the parity only matters for the
-                // banks: an entry in the "wrong" stream costs its gathers a two-way conflict; ~1 in 10 moves),
-                // then pad to a whole number of words.
-                {
-                    const bool a_long = nA > nB;
-                    const uint32_t ns = a_long ? nA : nB, nd = a_long ? nB : nA;
-                    const uint32_t src = sL + (a_long ? offA : offB), dst = sL + (a_long ? offB : offA);
-                    const uint32_t mv = min(8u, (ns - nd) >> 1);                // (loads first: their latencies overlap)
-                    uint32_t e[8];
-#pragma unroll
-                    for (uint32_t u = 0; u < 8u; ++u) if (u < mv) e[u] = lds_u8(src + 2u * (ns - 1u - u));
-#pragma unroll
-                    for (uint32_t u = 0; u < 8u; ++u) if (u < mv) sts_u8(dst + 2u * (nd + u), e[u]);
-                    nA = a_long ? ns - mv : nd + mv;
-                    nB = a_long ? nd + mv : ns - mv;
-                }
-                const uint32_t n2f = (2u * max(nA, nB) + 2u) & ~3u;             // 2 x pairs I hand to the force walk
-                for (uint32_t k = 2u * nA; k < n2f; k += 2u) sts_u8(sL + offA + k, M_DUMMY);
-                for (uint32_t k = 2u * nB; k < n2f; k += 2u) sts_u8(sL + offB + k, M_DUMMY + 1);
-                const int nw = (int)(n2f >> 2);
+                const int nw = (int)(n2 >> 2);                  // (levelled and padded above)
                 const int rows = __reduce_max_sync(0xffffffffu, nw) + 1;
                 int row = 0;
                 if (lane == 0) {
