@@ -72,6 +72,7 @@ struct tisph_ctx {
     int items_cap = 0;
     int pool_rows_cap = 0;
     int occ_dl = 0, occ_fl = 0;        // resident CTAs per SM of the two list kernels
+    int arena_rows = 0;                // list-pool rows a CTA of the density walk takes at a time
     int* item_row = nullptr;
     StepCounters* ctr = nullptr;
     int *fb_d = nullptr, *fb_f = nullptr;
@@ -344,7 +345,7 @@ static int run_density(tisph_ctx* c) {
     c->sp.ghost_walk = (c->sp.density_mode == 0 && c->sp.volume_mode == 0) ? 0 : 1;
     auto kd = c->sp.volume_mode == 1 ? k_density_list<true> : k_density_list<false>;
     kd<<<c->grid_dl, NB_THREADS, c->sp.volume_mode == 1 ? DL_SMEM_AKINCI : DL_SMEM, st>>>(
-        c->sp, c->cell_end, c->items, c->ctr, c->pool_rows_cap, c->variant == 1, c->P[b], c->V[b], c->Q[b],
+        c->sp, c->cell_end, c->items, c->ctr, c->pool_rows_cap, c->arena_rows, c->variant == 1, c->P[b], c->V[b], c->Q[b],
         c->D, c->S, c->ncount, c->Lg, c->item_row, c->item_flags, c->fb_d, c->fb_f);
     k_density_fb<<<c->grid_dfb, NB_THREADS, DF_SMEM, st>>>(c->sp, c->cell_end, c->items, c->ctr, c->fb_d,
                                                           c->P[b], c->V[b], c->Q[b], c->D, c->S, c->ncount);
@@ -448,7 +449,7 @@ int tisph_create(const tisph_config* cfg, tisph_ctx** out) {
     // words of its longest lane: ~12 rows at the reference spacing, i.e. ~0.4 KB per particle; sized for
     // 0.75 KB per particle plus slack.  Items that find the pool exhausted take the fallback force kernel.
     {
-        int64_t rows = cfg->generation == 1 ? 1 : (int64_t)cap * 6 + 65536;
+        int64_t rows = cfg->generation == 1 ? 1 : (int64_t)cap * 6 + 592 * 4 * ARENA_MIN;
         c->pool_rows_cap = (int)(rows < 0x7fffffff / 2 ? rows : 0x7fffffff / 2);
     }
     A(dalloc(&c->Lg, (size_t)c->pool_rows_cap * 32));
@@ -476,6 +477,10 @@ int tisph_create(const tisph_config* cfg, tisph_ctx** out) {
         A(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_density_list<false>, NB_THREADS, DL_SMEM));
         c->grid_dl = sms * (occ > 0 ? occ : 1);
         c->occ_dl = occ;
+        // every CTA holds at most one partly used chunk: small pools hand out small chunks
+        c->arena_rows = c->pool_rows_cap / (4 * c->grid_dl);
+        if (c->arena_rows > ARENA_ROWS) c->arena_rows = ARENA_ROWS;
+        if (c->arena_rows < 2 * ARENA_MIN) c->arena_rows = 2 * ARENA_MIN;
         A(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_force_list<true>, NB_THREADS, FL_SMEM));
         c->grid_fl = sms * (occ > 0 ? occ : 1);
         c->occ_fl = occ;

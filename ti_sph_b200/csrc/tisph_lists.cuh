@@ -112,6 +112,8 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
 // =======================================================================================
 constexpr int LIST_T = LSTRIDE / 4;              // 25 words
 constexpr int LIST_J = PASS_T * LIST_T + 4;      // 804 words: = 4 (mod 32)
+constexpr int ARENA_ROWS = 4096;                 // rows (512 KiB) a CTA takes from the list pool at a time (fewer for small pools)
+constexpr int ARENA_MIN = GL * (LCAP2 / 2 + 1);  // ... and at least what one pass can need
 constexpr float HCUT = 1.0f + 7.0f / 1024.0f;    // filter threshold on the half-precision d2 / h^2 (see above)
 constexpr size_t DL_SMEM = (size_t)(LT_ROWS / 2) * 8 * (sizeof(uint4) + sizeof(uint2)) + (size_t)LT_SLOTS * (sizeof(float2) + sizeof(float)) +
                            (size_t)GL * LIST_J * 4 + (size_t)NB_THREADS * 2;
@@ -136,7 +138,7 @@ __device__ __forceinline__ void filter_rows(__half2 xi, __half2 yi, __half2 zi, 
 template <bool AKINCI>
 __global__ void __launch_bounds__(NB_THREADS, 3)
 k_density_list(SimParams sp, const int* __restrict__ cell_end, const int2* __restrict__ items,
-               StepCounters* __restrict__ ctr, int pool_rows_cap, int all_to_fallback,
+               StepCounters* __restrict__ ctr, int pool_rows_cap, int arena_rows, int all_to_fallback,
                const float4* __restrict__ P, float4* __restrict__ V, const float4* __restrict__ Q,
                float4* __restrict__ D, float* __restrict__ S, int* __restrict__ ncount,
                uint32_t* __restrict__ Lg, int* __restrict__ item_row, unsigned char* __restrict__ flags,
@@ -151,10 +153,11 @@ k_density_list(SimParams sp, const int* __restrict__ cell_end, const int2* __res
     int* GM = reinterpret_cast<int*>(LC + NB_THREADS);
     __shared__ CellRanges R;
     __shared__ ItemMeta M;
-    __shared__ int s_over;
+    __shared__ int s_over, s_arena[2];               // s_arena: next free row / end of this CTA's chunk of the list pool
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n_items = ctr->n_items;
+    if (tid < 2) s_arena[tid] = 0;
     const float2 one2 = make_float2(sp.one, sp.one);       // see the drain: keeps ptxas from contracting the exact sum
     const __half2 ncut = __float2half2_rn(-HCUT);
     // ---- filter arrangement: lane jF = warp, target tF = lane
@@ -237,6 +240,21 @@ k_density_list(SimParams sp, const int* __restrict__ cell_end, const int2* __res
         bool redo = false;
 
         for (int pass = 0; pass < npass; ++pass) {
+            // the drain's target (arrangement: target tid / 8): asked for now, needed after the filter
+            const int t_local = pass * PASS_T + tD;
+            const int i = G.i0 + t_local;
+            const bool active = t_local < G.nT;
+            const float4 pi = active ? P[i] : make_float4(-FAR, -FAR, -FAR, 0.f);
+            const int mat_i = active ? __float_as_int(Q[i].z) : MAT_FLUID;
+            if (tid == 0 && own) {
+                // list rows come from a per-CTA arena refilled here, behind the filter, so that the warps reserve
+                // theirs with a shared-memory atomic (a pass needs at most 8 x (1 + LCAP2 / 2) rows)
+                if (s_arena[1] - s_arena[0] < GL * (LCAP2 / 2 + 1)) {
+                    const int base = atomicAdd(&ctr->pool_rows, arena_rows);
+                    s_arena[0] = base;
+                    s_arena[1] = base + arena_rows <= pool_rows_cap ? base + arena_rows : base;   // exhausted: an empty arena
+                }
+            }
             // ======== FILTER: my target against the candidates of lane `warp` ==============================
             int ovf = 0;
             {
@@ -273,11 +291,7 @@ k_density_list(SimParams sp, const int* __restrict__ cell_end, const int2* __res
             }
             if (__syncthreads_or(ovf)) { redo = true; break; }
             // ======== DRAIN: target tid / 8, lane tid % 8 ====================================================
-            const int t_local = pass * PASS_T + tD;
-            const int i = G.i0 + t_local;
-            const bool active = t_local < G.nT;
-            const float4 pi = active ? P[i] : make_float4(-FAR, -FAR, -FAR, 0.f);
-            // my own slot in the tile, if this lane owns it
+            // the target's own slot in the tile
             const int self_t = (active && walk_total > 0 && i >= self_lo && i < self_lo + self_len) ? R.off[4] + (i - self_lo) : -1;
             const int self_s = self_t >= 0 ? cand_to_slot(self_t) : -1;
             float2 wsum2 = make_float2(0.f, 0.f);
@@ -286,19 +300,21 @@ k_density_list(SimParams sp, const int* __restrict__ cell_end, const int2* __res
             // the filter thread of (target tD, lane j) was thread 32 j + tD
             const uint32_t nab = LC[32 * j + tD];
             uint32_t nA = nab & 0xffu, nB = nab >> 8;
-            if (self_s >= 0 && (self_s & 7) == j) {
-                // p_i != p_j (partice_systemv4.py:344): the target itself passed the filter (d2 = 0).  Its stream
-                // is ascending, so a binary search finds the entry; the stream's dummy row takes its place.
-                const uint32_t ms = (uint32_t)self_s >> 3;
-                const uint32_t sb = sL + ((ms & 1u) ? offB : offA);
-                uint32_t lo = 0, hi = (ms & 1u) ? nB : nA;
-                while (lo < hi) {
-                    const uint32_t mid = (lo + hi) >> 1;
-                    if (lds_u8(sb + 2u * mid) < ms) lo = mid + 1u; else hi = mid;
+            if (self_s >= 0) {
+                // p_i != p_j (partice_systemv4.py:344): the target itself passed the filter (d2 = 0) and sits in the
+                // list of lane (self_s & 7).  The 8 lanes of the group look for it together, each in every 8th
+                // entry of that stream (independent loads); the one that finds it puts the dummy row in its place.
+                const uint32_t ms = (uint32_t)self_s >> 3, js = (uint32_t)self_s & 7u;
+                const uint32_t nss = LC[32 * js + tD];
+                const uint32_t ns = (ms & 1u) ? nss >> 8 : nss & 0xffu;
+                const uint32_t sb = smem_u32(L) + 4u * (LIST_J * js + LIST_T * tD) + ((ms & 1u) ? offB : offA);
+#pragma unroll
+                for (uint32_t r8 = 0; r8 < (uint32_t)LCAP2; r8 += 8u) {
+                    const uint32_t k = r8 + (uint32_t)j;
+                    if (k < ns && lds_u8(sb + 2u * k) == ms) sts_u8(sb + 2u * k, M_DUMMY + (ms & 1u));
                 }
-                TISPH_CHECK(lo < ((ms & 1u) ? nB : nA) && lds_u8(sb + 2u * lo) == ms);
-                sts_u8(sb + 2u * lo, M_DUMMY + (ms & 1u));
             }
+            __syncwarp();
             // The two streams are consumed in lockstep (here and in the force walk), so the longer one sets the
             // number of iterations: level them by moving tail entries across (the parity only matters for the
             // banks: an entry in the "wrong" stream costs its gathers a two-way conflict; ~1 in 10 moves).
@@ -369,8 +385,8 @@ k_density_list(SimParams sp, const int* __restrict__ cell_end, const int2* __res
                 const int rows = __reduce_max_sync(0xffffffffu, nw) + 1;
                 int row = 0;
                 if (lane == 0) {
-                    row = atomicAdd(&ctr->pool_rows, rows);
-                    if (row + rows > pool_rows_cap) { row = -1; s_over = 1; }   // pool exhausted: fallback force kernel
+                    row = atomicAdd(&s_arena[0], rows);
+                    if (row + rows > s_arena[1]) { row = -1; s_over = 1; }     // pool exhausted: fallback force kernel
                     item_row[(2 * it + pass) * 8 + warp] = row;
                 }
                 row = __shfl_sync(0xffffffffu, row, 0);
@@ -392,7 +408,7 @@ k_density_list(SimParams sp, const int* __restrict__ cell_end, const int2* __res
                 if (AKINCI) wbsum += __shfl_xor_sync(0xffffffffu, wbsum, o);
             }
             if (j == 0 && active)
-                density_epilogue(sp, i, pi.w, __float_as_int(Q[i].z), wsum, wbsum, cnt, V, Q, D, S, ncount);
+                density_epilogue(sp, i, pi.w, mat_i, wsum, wbsum, cnt, V, Q, D, S, ncount);
             __syncthreads();                                   // the lists are free for the next pass; s_over is complete
         }
         if (tid == 0) {
@@ -505,7 +521,7 @@ k_force_list(SimParams sp, const int* __restrict__ cell_end, const int2* __restr
     }
 
     ItemFetch nx;
-    if (tid < 32) nx = fetch_item(sp, cell_end, items, n_items, &ctr->work_f);
+    if (tid < 32) nx = fetch_item(sp, cell_end, items, n_items, &ctr->work_f, flags);
     for (;;) {
         __syncthreads();                                 // everyone is done with the previous item's shared state
         if (tid < 32) publish_item(nx, R, M);
@@ -514,8 +530,8 @@ k_force_list(SimParams sp, const int* __restrict__ cell_end, const int2* __restr
         if (it >= n_items) break;
         ItemGeom G;
         item_geometry(M, R, G);
-        if (tid < 32) nx = fetch_item(sp, cell_end, items, n_items, &ctr->work_f);   // the next item, behind this one's walk
-        if (flags[it]) continue;                         // handled by k_force_fb
+        if (tid < 32) nx = fetch_item(sp, cell_end, items, n_items, &ctr->work_f, flags);   // the next item, behind this one's walk
+        if (M.flag) continue;                            // handled by k_force_fb
         if (G.c < sp.own_key_lo || G.c >= sp.own_key_hi) continue;   // ghost cell: not advanced here
         TISPH_CHECK(G.total <= LT_CAP);
         const int npass = (G.nT + PASS_T - 1) / PASS_T;

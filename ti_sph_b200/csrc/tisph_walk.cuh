@@ -198,12 +198,14 @@ __device__ __forceinline__ int next_item(int* cursor, int* s_slot) {
 struct ItemFetch {
     int it;         // item index (>= n_items: the list is exhausted)
     int2 item;
-    int a, b;       // lane < 9: first sorted index / length of range `lane`;  lane 9: first / end index of the cell
+    int a, b;       // lane < 9: first sorted index / length of range `lane`;  lane 9: first / end index of the cell;
+                    // lane 10: a = the item's flag (force walk)
 };
-struct ItemMeta { int it, cell, first, tb, te; };
+struct ItemMeta { int it, cell, first, tb, te, flag; };
 
 __device__ __forceinline__ ItemFetch fetch_item(const SimParams& sp, const int* __restrict__ cell_end,
-                                                const int2* __restrict__ items, int n_items, int* cursor) {
+                                                const int2* __restrict__ items, int n_items, int* cursor,
+                                                const unsigned char* __restrict__ flags = nullptr) {
     const int lane = threadIdx.x & 31;
     ItemFetch f;
     int it = 0;
@@ -226,6 +228,8 @@ __device__ __forceinline__ ItemFetch fetch_item(const SimParams& sp, const int* 
         } else if (lane == 9) {
             f.a = cell_start(cell_end, c);
             f.b = cell_end[c];
+        } else if (lane == 10 && flags) {
+            f.a = flags[f.it];
         }
     }
     return f;
@@ -239,6 +243,7 @@ __device__ __forceinline__ void publish_item(const ItemFetch& f, CellRanges& R, 
     if (lane < 9) { R.gb[lane] = f.a; R.off[lane] = inc - len; }
     if (lane == 8) R.off[9] = inc;
     if (lane == 9) { M.tb = f.a; M.te = f.b; }
+    if (lane == 10) M.flag = f.a;
     if (lane == 0) { M.it = f.it; M.cell = f.item.x; M.first = f.item.y; }
 }
 
