@@ -739,6 +739,7 @@ int tisph_download(tisph_ctx* c, int32_t field, void* dst, size_t bytes) {
     int n = c->o_hi - c->o_lo, dim = c->cfg.dim, cur = c->cur;
     const float4* src = nullptr;
     int comp0 = 0, ncomp = 1;
+    float floor_x = -INFINITY;
     const void* direct = nullptr;   // already in the reference layout on the device
     size_t count = (size_t)n;
     switch (field) {
@@ -746,7 +747,11 @@ int tisph_download(tisph_ctx* c, int32_t field, void* dst, size_t bytes) {
         case TISPH_F_V: src = c->V[cur]; comp0 = 0; ncomp = dim; break;
         case TISPH_F_MASS: src = c->P[cur]; comp0 = 3; break;
         case TISPH_F_VOLUME: src = c->V[cur]; comp0 = 3; break;
-        case TISPH_F_DENSITY: if (c->phase == 2) { src = c->D; comp0 = 2; } else { src = c->Q[cur]; comp0 = 0; } break;
+        case TISPH_F_DENSITY:          // between the density and the force stage: the clamped density of the D scratch
+            if (c->phase == 2 && c->cfg.generation == 1) { src = c->D; comp0 = 2; }
+            else if (c->phase == 2) { src = c->D; comp0 = 0; floor_x = c->sp.rho0; }
+            else { src = c->Q[cur]; comp0 = 0; }
+            break;
         case TISPH_F_PRESSURE: if (c->phase == 2) { src = c->D; comp0 = 3; } else { src = c->Q[cur]; comp0 = 1; } break;
         case TISPH_F_MATERIAL: src = c->Q[cur]; comp0 = 2; break;
         case TISPH_F_ORIG_ID: src = c->Q[cur]; comp0 = 3; break;
@@ -789,7 +794,7 @@ int tisph_download(tisph_ctx* c, int32_t field, void* dst, size_t bytes) {
         if (field == TISPH_F_COLOR)
             k_gather_color<<<nblocks(n, 256), 256, 0, st>>>(n, ncomp, c->Q[cur] + off, c->color, (int*)c->staging);
         else
-            k_unpack<<<nblocks(n, 256), 256, 0, st>>>(n, src, comp0, ncomp, (uint32_t*)c->staging);
+            k_unpack<<<nblocks(n, 256), 256, 0, st>>>(n, src, comp0, ncomp, (uint32_t*)c->staging, floor_x);
         c->launches += 1;
         CU(cudaGetLastError());
         CU(cudaMemcpyAsync(dst, c->staging, need, cudaMemcpyDeviceToHost, st));

@@ -282,12 +282,14 @@ k_upload_xv(int n, int dim, const float* __restrict__ pos, const float* __restri
     P[i] = p; V[i] = v;
 }
 
-// dst[i*ncomp + k] = word (comp0+k) of src[i]; 32-bit words, so f32 and i32 alike
+// dst[i*ncomp + k] = word (comp0+k) of src[i]; 32-bit words, so f32 and i32 alike.  floor_x > -inf: the x
+// component is raised to floor_x first (the clamped density max(rho, rho0) of wcsphv2.py:46)
 __global__ void __launch_bounds__(256)
-k_unpack(int n, const float4* __restrict__ src, int comp0, int ncomp, uint32_t* __restrict__ dst) {
+k_unpack(int n, const float4* __restrict__ src, int comp0, int ncomp, uint32_t* __restrict__ dst, float floor_x) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     float4 s = src[i];
+    s.x = fmaxf(s.x, floor_x);
     uint32_t w[4] = {__float_as_uint(s.x), __float_as_uint(s.y), __float_as_uint(s.z),
                      __float_as_uint(s.w)};
     for (int k = 0; k < ncomp; ++k) dst[(size_t)i * ncomp + k] = w[comp0 + k];

@@ -151,8 +151,8 @@ k_density_list(SimParams sp, const int* __restrict__ cell_end, const int2* __res
     unsigned char* L = reinterpret_cast<unsigned char*>(GZ + LT_SLOTS);
     unsigned short* LC = reinterpret_cast<unsigned short*>(L + GL * LIST_J * 4);     // entries per stream: nA | nB << 8
     int* GM = reinterpret_cast<int*>(LC + NB_THREADS);
-    __shared__ CellRanges R;
-    __shared__ ItemMeta M;
+    __shared__ CellRanges R2[2];                     // current item / the one being published (see tisph_walk.cuh)
+    __shared__ ItemMeta M2[2];
     __shared__ int s_over, s_arena[2];               // s_arena: next free row / end of this CTA's chunk of the list pool
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -177,11 +177,14 @@ k_density_list(SimParams sp, const int* __restrict__ cell_end, const int2* __res
     if (AKINCI && tid < 16) GM[8 * M_DUMMY + tid] = MAT_FLUID;
 
     ItemFetch nx;
-    if (warp == 0) nx = fetch_item(sp, cell_end, items, n_items, &ctr->work_d);
-    for (;;) {
-        __syncthreads();                                   // everyone is done with the previous item's shared state
-        if (warp == 0) publish_item(nx, R, M);
-        __syncthreads();
+    if (warp == 0) {
+        nx = fetch_item(sp, cell_end, items, n_items, &ctr->work_d);
+        publish_item(nx, R2[0], M2[0]);
+    }
+    __syncthreads();
+    for (int buf = 0;; buf ^= 1) {
+        const CellRanges& R = R2[buf];
+        const ItemMeta& M = M2[buf];
         const int it = M.it;
         if (it >= n_items) break;
         ItemGeom G;
@@ -193,6 +196,8 @@ k_density_list(SimParams sp, const int* __restrict__ cell_end, const int2* __res
                 fb_d[atomicAdd(&ctr->n_fb_d, 1)] = it;
                 fb_f[atomicAdd(&ctr->n_fb_f, 1)] = it;
             }
+            if (warp == 0) publish_item(nx, R2[buf ^ 1], M2[buf ^ 1]);
+            __syncthreads();
             continue;
         }
         const bool own = G.c >= sp.own_key_lo && G.c < sp.own_key_hi;   // ghost cells get no force walk
@@ -421,6 +426,9 @@ k_density_list(SimParams sp, const int* __restrict__ cell_end, const int2* __res
                 if (s_over && own) fb_f[atomicAdd(&ctr->n_fb_f, 1)] = it;
             }
         }
+        // the one barrier between two items: the next item's ranges go to the other buffer, which nobody reads now
+        if (warp == 0) publish_item(nx, R2[buf ^ 1], M2[buf ^ 1]);
+        __syncthreads();
     }
 }
 
@@ -506,8 +514,8 @@ k_force_list(SimParams sp, const int* __restrict__ cell_end, const int2* __restr
     float2* V01 = P23 + LT_SLOTS;
     float2* V23 = V01 + LT_SLOTS;
     float* PR = reinterpret_cast<float*>(V23 + LT_SLOTS);
-    __shared__ CellRanges R;
-    __shared__ ItemMeta M;
+    __shared__ CellRanges R2[2];                     // current item / the one being published
+    __shared__ ItemMeta M2[2];
     const int tid = threadIdx.x;
     const int j = tid & (GL - 1);
     const int n_items = ctr->n_items;
@@ -521,42 +529,47 @@ k_force_list(SimParams sp, const int* __restrict__ cell_end, const int2* __restr
     }
 
     ItemFetch nx;
-    if (tid < 32) nx = fetch_item(sp, cell_end, items, n_items, &ctr->work_f, flags);
-    for (;;) {
-        __syncthreads();                                 // everyone is done with the previous item's shared state
-        if (tid < 32) publish_item(nx, R, M);
-        __syncthreads();
+    if (tid < 32) {
+        nx = fetch_item(sp, cell_end, items, n_items, &ctr->work_f, flags);
+        publish_item(nx, R2[0], M2[0]);
+    }
+    __syncthreads();
+    for (int buf = 0;; buf ^= 1) {
+        const CellRanges& R = R2[buf];
+        const ItemMeta& M = M2[buf];
         const int it = M.it;
         if (it >= n_items) break;
         ItemGeom G;
         item_geometry(M, R, G);
         if (tid < 32) nx = fetch_item(sp, cell_end, items, n_items, &ctr->work_f, flags);   // the next item, behind this one's walk
-        if (M.flag) continue;                            // handled by k_force_fb
-        if (G.c < sp.own_key_lo || G.c >= sp.own_key_hi) continue;   // ghost cell: not advanced here
+        // items of k_force_fb, and ghost cells (not advanced here), are passed over
+        if (M.flag || G.c < sp.own_key_lo || G.c >= sp.own_key_hi) {
+            if (tid < 32) publish_item(nx, R2[buf ^ 1], M2[buf ^ 1]);
+            __syncthreads();
+            continue;
+        }
         TISPH_CHECK(G.total <= LT_CAP);
         const int npass = (G.nT + PASS_T - 1) / PASS_T;
         // my warp's rows of the list pool, one block per pass: asked for now, needed after the staging
         const int row_p0 = item_row[(2 * it) * 8 + (tid >> 5)];
         const int row_p1 = npass > 1 ? item_row[(2 * it + 1) * 8 + (tid >> 5)] : row_p0;
         // ---- stage the tile: candidate e in slot cand_to_slot(e); two candidates per thread and round,
-        //      all eight loads in flight before the first store
+        //      all six loads in flight before the first store (psi comes ready-made from the density walk: D.z)
         for (int e0 = tid; e0 < G.total; e0 += 2 * NB_THREADS) {
             const int e1 = e0 + NB_THREADS;
             const bool two = e1 < G.total;
             const int g0 = tile_to_global(R, e0), g1 = two ? tile_to_global(R, e1) : g0;
-            const float4 p0 = Pin[g0], v0 = Vin[g0], d0 = D[g0], q0 = Qin[g0];
-            const float4 p1 = Pin[g1], v1 = Vin[g1], d1 = D[g1], q1 = Qin[g1];
+            const float4 p0 = Pin[g0], v0 = Vin[g0], d0 = D[g0];
+            const float4 p1 = Pin[g1], v1 = Vin[g1], d1 = D[g1];
             {
-                const float psi = __float_as_int(q0.z) != MAT_FLUID ? -v0.w : p0.w;
                 const int sl = cand_to_slot(e0);
-                P01[sl] = make_float2(p0.x, p0.y); P23[sl] = make_float2(p0.z, psi);
+                P01[sl] = make_float2(p0.x, p0.y); P23[sl] = make_float2(p0.z, d0.z);
                 V01[sl] = make_float2(v0.x, v0.y); V23[sl] = make_float2(v0.z, d0.x);
                 PR[sl] = d0.y;
             }
             if (two) {
-                const float psi = __float_as_int(q1.z) != MAT_FLUID ? -v1.w : p1.w;
                 const int sl = cand_to_slot(e1);
-                P01[sl] = make_float2(p1.x, p1.y); P23[sl] = make_float2(p1.z, psi);
+                P01[sl] = make_float2(p1.x, p1.y); P23[sl] = make_float2(p1.z, d1.z);
                 V01[sl] = make_float2(v1.x, v1.y); V23[sl] = make_float2(v1.z, d1.x);
                 PR[sl] = d1.y;
             }
@@ -577,7 +590,7 @@ k_force_list(SimParams sp, const int* __restrict__ cell_end, const int2* __restr
             const bool active = t_local < G.nT;
             const float4 pi = active ? Pin[i] : make_float4(-FAR, -FAR, -FAR, 1.f);
             const float4 vi = active ? Vin[i] : make_float4(0.f, 0.f, 0.f, 0.f);
-            const float4 di = active ? D[i] : make_float4(1.f, 0.f, 1.f, 0.f);
+            const float4 di = active ? D[i] : make_float4(1.f, 0.f, 0.f, 0.f);
             const float4 qi = active ? Qin[i] : make_float4(0.f, 0.f, 0.f, 0.f);
             const bool walker = active && __float_as_int(qi.z) == MAT_FLUID;
             const float coh_kw = 0.01f / pi.w * sp.k_w;                // wcsphv2.py:64 (x the kernel normalisation)
@@ -621,6 +634,9 @@ k_force_list(SimParams sp, const int* __restrict__ cell_end, const int2* __restr
                 force_epilogue(sp, i, walker, pi, vi, di, qi, a6[0], a6[1], a6[2], a6[3], a6[4], a6[5],
                                Pout, Vout, Qout, dvel, a_np_out, a_p_out);
         }
+        // the one barrier between two items: the next item's ranges go to the other buffer, which nobody reads now
+        if (tid < 32) publish_item(nx, R2[buf ^ 1], M2[buf ^ 1]);
+        __syncthreads();
     }
 }
 

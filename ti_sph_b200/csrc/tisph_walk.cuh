@@ -78,7 +78,7 @@ __device__ __forceinline__ void density_epilogue(const SimParams& sp, int i, flo
                                                  float4* __restrict__ V, const float4* __restrict__ Q,
                                                  float4* __restrict__ D, float* __restrict__ S,
                                                  int* __restrict__ ncount) {
-    float rho_raw, s_i = 0.f;
+    float rho_raw, s_i = 0.f, psi = mass_i;           // psi: what a neighbour's pair terms are weighted with
     if (mat_i == MAT_FLUID) {
         float self = mass_i * sp.k_w;                  // mass_i * W(0)
         s_i = mass_i * (sp.k_w * wsum);                // sum_j mass_i W(r_ij)   (Q2)
@@ -89,10 +89,12 @@ __device__ __forceinline__ void density_epilogue(const SimParams& sp, int i, flo
         float4 vi = V[i];
         vi.w = 1.0f / delta;
         V[i] = vi;
+        psi = -vi.w;                                   // boundary neighbours enter with their volume
     }
     float rho_c = fmaxf(rho_raw, sp.rho0);                                                       // :46
     float pr = sp.stiffness * (eos_pow(rho_c / sp.rho0, sp.exponent, sp.int_exponent) - 1.0f);   // :47
-    D[i] = make_float4(rho_raw, pr / (rho_c * rho_c), rho_c, pr);
+    // D = {unclamped density, p / rho_c^2, psi (+mass | -volume), p}; the clamped density is max(D.x, rho0)
+    D[i] = make_float4(rho_raw, pr / (rho_c * rho_c), psi, pr);
     S[i] = s_i;
     ncount[i] = cnt;
 }
@@ -151,7 +153,7 @@ __device__ __forceinline__ void force_epilogue(const SimParams& sp, int i, bool 
     }
     Pout[i] = pout;
     Vout[i] = vout;
-    Qout[i] = make_float4(di.z, di.w, qi.z, qi.w);     // clamped rho, p, material, orig id
+    Qout[i] = make_float4(fmaxf(di.x, sp.rho0), di.w, qi.z, qi.w);     // clamped rho (wcsphv2.py:46), p, material, orig id
     dvel[i] = acc;
 }
 
