@@ -91,15 +91,22 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
 // Walk 1: boundary volume, density summation, clamp, Tait EOS; builds the neighbour lists
 //
 // FILTER tile, half precision.  The filter only has to find a SUPERSET of the neighbours (the drain applies
-// the exact IEEE test), so it runs on binary16 copies of the positions: u = (x - cell centre) / h, rounded
-// to half, |u| <= 1.5 for every candidate.  For a pair within the cutoff the half-precision distance
-// differs from the true one by at most 5.3e-3 (coordinates: 1.2e-4 target + 4.9e-4 candidate + 4.9e-4
-// difference per component, 2 sqrt(3) x that on d2; three roundings of 4.9e-4 in the sum), so accepting
-// d2_half < 1 + 7/1024 = 1.0068 loses nobody and lets ~1 % extra candidates through (they fail the exact
-// test in the drain and evaluate to exact zeros in the force walk).  Two rows (m = 2k, 2k+1: slots 16k+j,
-// 16k+8+j) are the two halves of a half2; the row pairs k = 2kk, 2kk+1 of lane class j are one 24-byte record:
-//   HA[8 kk + j] = {x(2kk), y(2kk), z(2kk), x(2kk+1)}   HB[8 kk + j] = {y(2kk+1), z(2kk+1)}      (half2 each, NEGATED)
-// Half the bytes and half the FMA-pipe time of the f32x2 filter of round 1.
+// the exact IEEE test), so it runs on binary16 copies of the positions, u = (x - cell centre) / h rounded to
+// half (|u| <= 1.5 for every candidate, <= 0.5 for a target), in the form
+//     n_j - 2 u_i.u_j  <  T_i         n_j = |u_j|^2 of the ROUNDED u_j, rounded to half;   T_i = HC2 - |u_i|^2
+// as three chained HFMA2 (z, y, x) and one HSETP2 per two rows -- no differences to form.  Error budget FOR A PAIR
+// WITHIN THE CUTOFF (only those must not be lost): the rounded positions are at most sqrt(3) (2^-13 + 2^-11) =
+// 1.07e-3 further apart than the true ones (d2 < 1.00215); |u_j| < 1.87, so n_j < 4 is rounded by at most 2^-10;
+// the partial sums are d2 - n_i plus at most two products of magnitude <= 1.5, i.e. below 4, 4 and 2 in
+// magnitude: roundings of at most 2^-10, 2^-10, 2^-11 (the products inside an FMA are exact); T_i is rounded UP.
+// Total 1.00215 + 3.4e-3 = 1.0056 < HC2 = 1.0068 = 1 + 7/1024.  A pair outside the cutoff may pass with a
+// larger error (big n_j): it fails the exact test in the drain and evaluates to exact zeros in the force walk
+// (~1 % extra candidates).  Padding rows carry n = 60000, idle targets T = -60000: never a survivor.
+// Two rows (m = 2k, 2k+1: slots 16k+j, 16k+8+j) are the two halves of a half2; one 16-byte record per row pair k
+// and lane class j:
+//   T4[8 k + j] = {x(2k) x(2k+1), y(2k) y(2k+1), z(2k) z(2k+1), n(2k) n(2k+1)}
+// Entries of the ODD stream hold the EVEN row of their pair (row = entry + 1): one register serves both pushes,
+// and the walks add the row offset to the odd stream's base address for free.
 // DRAIN planes, single precision:  GXY[s] = {x,y}, GZ[s] = z of slot s;  GM[s] = material (Akinci volumes only)
 //
 // A pass runs in two phases with different thread arrangements over the same (target, lane) lists:
@@ -114,25 +121,25 @@ constexpr int LIST_T = LSTRIDE / 4;              // 25 words
 constexpr int LIST_J = PASS_T * LIST_T + 4;      // 804 words: = 4 (mod 32)
 constexpr int ARENA_ROWS = 4096;                 // rows (512 KiB) a CTA takes from the list pool at a time (fewer for small pools)
 constexpr int ARENA_MIN = GL * (LCAP2 / 2 + 1);  // ... and at least what one pass can need
-constexpr float HCUT = 1.0f + 7.0f / 1024.0f;    // filter threshold on the half-precision d2 / h^2 (see above)
-constexpr size_t DL_SMEM = (size_t)(LT_ROWS / 2) * 8 * (sizeof(uint4) + sizeof(uint2)) + (size_t)LT_SLOTS * (sizeof(float2) + sizeof(float)) +
+constexpr float HC2 = 1.0f + 7.0f / 1024.0f;     // filter threshold on the half-precision d2 / h^2 (see above)
+constexpr float N_NEVER = 60000.0f;              // n of padding rows, -T of idle targets (finite in half precision)
+constexpr size_t DL_SMEM = (size_t)LT_ROWS * 8 * sizeof(uint4) + (size_t)LT_SLOTS * (sizeof(float2) + sizeof(float)) +
                            (size_t)GL * LIST_J * 4 + (size_t)NB_THREADS * 2;
 constexpr size_t DL_SMEM_AKINCI = DL_SMEM + (size_t)LT_SLOTS * sizeof(int);
 
 __device__ __forceinline__ uint32_t h2_bits(__half2 v) { return *reinterpret_cast<uint32_t*>(&v); }
 __device__ __forceinline__ __half2 bits_h2(uint32_t v) { return *reinterpret_cast<__half2*>(&v); }
 
-// one row pair of the filter: s = |u_i - u_j|^2 - HCUT for the two rows (negative = survivor), then the
-// predicated pushes of the row bytes m, m+1 to the two pending streams
-__device__ __forceinline__ void filter_rows(__half2 xi, __half2 yi, __half2 zi, __half2 ncut, uint32_t nx, uint32_t ny,
-                                            uint32_t nz, uint32_t m, uint32_t& pA, uint32_t& pB) {
-    const __half2 dx = __hadd2(xi, bits_h2(nx)), dy = __hadd2(yi, bits_h2(ny)), dz = __hadd2(zi, bits_h2(nz));
-    const __half2 s = __hfma2(dz, dz, __hfma2(dy, dy, __hfma2(dx, dx, ncut)));
-    asm volatile("{\n\t.reg .pred p, q;\n\t.reg .b32 z;\n\tmov.b32 z, 0;\n\t"
-                 "setp.lt.f16x2 p|q, %2, z;\n\t"
-                 "@p st.shared.u8 [%0], %3;\n\t@p add.u32 %0, %0, 2;\n\t"
+// one row pair of the filter: s = n_j - 2 u_i.u_j for the two rows (xi, yi, zi hold -2 u_i; s < T = survivor),
+// then the predicated pushes of the pair's EVEN row byte m to the two pending streams
+__device__ __forceinline__ void filter_rows(__half2 xi, __half2 yi, __half2 zi, uint32_t T, uint4 rec, uint32_t m,
+                                            uint32_t& pA, uint32_t& pB) {
+    const __half2 s = __hfma2(xi, bits_h2(rec.x), __hfma2(yi, bits_h2(rec.y), __hfma2(zi, bits_h2(rec.z), bits_h2(rec.w))));
+    asm volatile("{\n\t.reg .pred p, q;\n\t"
+                 "setp.lt.f16x2 p|q, %2, %3;\n\t"
+                 "@p st.shared.u8 [%0], %4;\n\t@p add.u32 %0, %0, 2;\n\t"
                  "@q st.shared.u8 [%1], %4;\n\t@q add.u32 %1, %1, 2;\n\t}"
-                 : "+r"(pA), "+r"(pB) : "r"(h2_bits(s)), "r"(m), "r"(m + 1u) : "memory");
+                 : "+r"(pA), "+r"(pB) : "r"(h2_bits(s)), "r"(T), "r"(m) : "memory");
 }
 
 template <bool AKINCI>
@@ -144,9 +151,8 @@ k_density_list(SimParams sp, const int* __restrict__ cell_end, const int2* __res
                uint32_t* __restrict__ Lg, int* __restrict__ item_row, unsigned char* __restrict__ flags,
                int* __restrict__ fb_d, int* __restrict__ fb_f) {
     extern __shared__ float4 dyn_smem[];
-    uint4* HA = reinterpret_cast<uint4*>(dyn_smem);
-    uint2* HB = reinterpret_cast<uint2*>(HA + (LT_ROWS / 2) * 8);
-    float2* GXY = reinterpret_cast<float2*>(HB + (LT_ROWS / 2) * 8);
+    uint4* T4 = reinterpret_cast<uint4*>(dyn_smem);
+    float2* GXY = reinterpret_cast<float2*>(T4 + LT_ROWS * 8);
     float* GZ = reinterpret_cast<float*>(GXY + LT_SLOTS);
     unsigned char* L = reinterpret_cast<unsigned char*>(GZ + LT_SLOTS);
     unsigned short* LC = reinterpret_cast<unsigned short*>(L + GL * LIST_J * 4);     // entries per stream: nA | nB << 8
@@ -159,9 +165,8 @@ k_density_list(SimParams sp, const int* __restrict__ cell_end, const int2* __res
     const int n_items = ctr->n_items;
     if (tid < 2) s_arena[tid] = 0;
     const float2 one2 = make_float2(sp.one, sp.one);       // see the drain: keeps ptxas from contracting the exact sum
-    const __half2 ncut = __float2half2_rn(-HCUT);
     // ---- filter arrangement: lane jF = warp, target tF = lane
-    const uint32_t fHA = smem_u32(HA) + 16u * warp, fHB = smem_u32(HB) + 8u * warp;
+    const uint32_t fT = smem_u32(T4) + 16u * warp;
     const uint32_t fL = smem_u32(L) + 4u * (LIST_J * warp + LIST_T * lane);
     // a row-2k candidate goes to byte 2n + offA of the list, a row-2k+1 candidate to byte 2n + offB: the FIRST
     // entry of every byte pair has the parity of the target's drain group (target & 1)
@@ -169,7 +174,11 @@ k_density_list(SimParams sp, const int* __restrict__ cell_end, const int2* __res
     // ---- drain arrangement: target tid / 8, lane j = tid % 8
     const int j = tid & (GL - 1), tD = tid >> 3;
     const uint32_t c1 = tD & 1u;                           // parity of my group: which stream I consume first
-    const uint32_t sG = smem_u32(GXY) + 8u * j, sGZ = smem_u32(GZ) + 4u * j, sGM = smem_u32(GM) + 4u * j;
+    // plane addresses of my lane for the FIRST and the SECOND entry of a byte pair; the odd stream's entries name
+    // the even row of their pair, so its base is one row further (odd stream = second entry of an even group)
+    const uint32_t sG1 = smem_u32(GXY) + 8u * j + 64u * c1, sG2 = smem_u32(GXY) + 8u * j + 64u * (1u - c1);
+    const uint32_t sGZ1 = smem_u32(GZ) + 4u * j + 32u * c1, sGZ2 = smem_u32(GZ) + 4u * j + 32u * (1u - c1);
+    const uint32_t sGM1 = smem_u32(GM) + 4u * j + 32u * c1, sGM2 = smem_u32(GM) + 4u * j + 32u * (1u - c1);
     const uint32_t sL = smem_u32(L) + 4u * (LIST_J * j + LIST_T * tD);
     const uint32_t offA = c1, offB = 1u - c1;
     // the two dummy rows are FAR in every array, for good (half: |u| = 1000 makes d2 overflow to +inf)
@@ -215,27 +224,28 @@ k_density_list(SimParams sp, const int* __restrict__ cell_end, const int2* __res
             const int sa = 16 * k + jj, sb = sa + 8;                  // slots (rows 2k and 2k+1, lane class jj)
             const int ea = slot_to_cand(sa), eb = slot_to_cand(sb);
             float4 a = make_float4(FAR, FAR, FAR, 0.f), b = a;
-            float3 ua = make_float3(-1000.f, -1000.f, -1000.f), ub = ua;       // padding: never within the cutoff
+            float3 ua = make_float3(0.f, 0.f, 0.f), ub = ua;
+            bool va = false, vb = false;                                       // padding: never within the cutoff
             int ma = MAT_FLUID, mb = MAT_FLUID;
             if (ea < walk_total) {
                 const int g = tile_to_global(R, ea);
-                a = P[g];
+                a = P[g]; va = true;
                 ua = make_float3((a.x - ccx) * sp.inv_h, (a.y - ccy) * sp.inv_h, (a.z - ccz) * sp.inv_h);
                 if (AKINCI) ma = __float_as_int(Q[g].z);
             }
             if (eb < walk_total) {
                 const int g = tile_to_global(R, eb);
-                b = P[g];
+                b = P[g]; vb = true;
                 ub = make_float3((b.x - ccx) * sp.inv_h, (b.y - ccy) * sp.inv_h, (b.z - ccz) * sp.inv_h);
                 if (AKINCI) mb = __float_as_int(Q[g].z);
             }
             TISPH_CHECK(sb < LT_SLOTS && p < LT_ROWS * 8);
-            const uint32_t hx = h2_bits(__floats2half2_rn(-ua.x, -ub.x)), hy = h2_bits(__floats2half2_rn(-ua.y, -ub.y)),
-                           hz = h2_bits(__floats2half2_rn(-ua.z, -ub.z));
-            uint32_t* ha = reinterpret_cast<uint32_t*>(HA + 8 * (k >> 1) + jj);
-            uint32_t* hb = reinterpret_cast<uint32_t*>(HB + 8 * (k >> 1) + jj);
-            if ((k & 1) == 0) { ha[0] = hx; ha[1] = hy; ha[2] = hz; }
-            else { ha[3] = hx; hb[0] = hy; hb[1] = hz; }
+            // rounded coordinates and the norm of the ROUNDED vector (exact products in f32, one rounding to half)
+            const __half2 hx = __floats2half2_rn(ua.x, ub.x), hy = __floats2half2_rn(ua.y, ub.y), hz = __floats2half2_rn(ua.z, ub.z);
+            const float2 fx = __half22float2(hx), fy = __half22float2(hy), fz = __half22float2(hz);
+            const float na = va ? fmaf(fz.x, fz.x, fmaf(fy.x, fy.x, fx.x * fx.x)) : N_NEVER;
+            const float nb = vb ? fmaf(fz.y, fz.y, fmaf(fy.y, fy.y, fx.y * fx.y)) : N_NEVER;
+            T4[p] = make_uint4(h2_bits(hx), h2_bits(hy), h2_bits(hz), h2_bits(__floats2half2_rn(na, nb)));
             GXY[sa] = make_float2(a.x, a.y); GZ[sa] = a.z;
             GXY[sb] = make_float2(b.x, b.y); GZ[sb] = b.z;
             if (AKINCI) { GM[sa] = ma; GM[sb] = mb; }
@@ -264,30 +274,28 @@ k_density_list(SimParams sp, const int* __restrict__ cell_end, const int2* __res
             int ovf = 0;
             {
                 const int tf = pass * PASS_T + lane;
-                float3 uf = make_float3(1000.f, 1000.f, 1000.f);       // idle lane: far from everything
+                __half2 xi = __float2half2_rn(0.f), yi = xi, zi = xi;
+                uint32_t T = h2_bits(__float2half2_rn(-N_NEVER));      // idle lane: nothing survives
                 if (tf < G.nT) {
                     const float4 pf = P[G.i0 + tf];
-                    uf = make_float3((pf.x - ccx) * sp.inv_h, (pf.y - ccy) * sp.inv_h, (pf.z - ccz) * sp.inv_h);
+                    const __half hx = __float2half_rn((pf.x - ccx) * sp.inv_h), hy = __float2half_rn((pf.y - ccy) * sp.inv_h),
+                                 hz = __float2half_rn((pf.z - ccz) * sp.inv_h);
+                    const float fx = __half2float(hx), fy = __half2float(hy), fz = __half2float(hz);
+                    xi = __float2half2_rn(-2.0f * fx); yi = __float2half2_rn(-2.0f * fy); zi = __float2half2_rn(-2.0f * fz);   // (exact)
+                    T = h2_bits(__half2half2(__float2half_ru(HC2 - fmaf(fz, fz, fmaf(fy, fy, fx * fx)))));
                 }
-                const __half2 xi = __float2half2_rn(uf.x), yi = __float2half2_rn(uf.y), zi = __float2half2_rn(uf.z);
                 uint32_t pA = fA, pB = fB;                     // next free byte of the two pending streams
                 for (int k0 = 0; k0 < nrow2; k0 += FCHUNK) {
-                    // FCHUNK row pairs = FCHUNK / 2 records of 24 bytes; all loads first
-                    uint4 ra[FCHUNK / 2];
-                    uint2 rb[FCHUNK / 2];
+                    // FCHUNK row pairs = FCHUNK records of 16 bytes; all loads first
+                    uint4 rec[FCHUNK];
 #pragma unroll
-                    for (int u = 0; u < FCHUNK / 2; ++u) {
-                        const uint32_t kk = (uint32_t)(k0 >> 1) + u;
-                        asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(ra[u].x), "=r"(ra[u].y), "=r"(ra[u].z), "=r"(ra[u].w)
-                                     : "r"(fHA + 128u * kk) : "memory");
-                        asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(rb[u].x), "=r"(rb[u].y) : "r"(fHB + 64u * kk) : "memory");
-                    }
+                    for (int u = 0; u < FCHUNK; ++u)
+                        asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(rec[u].x), "=r"(rec[u].y), "=r"(rec[u].z), "=r"(rec[u].w)
+                                     : "r"(fT + 128u * (uint32_t)(k0 + u)) : "memory");
 #pragma unroll
-                    for (int u = 0; u < FCHUNK / 2; ++u) {
-                        const uint32_t m = 2u * (k0 + 2 * u);
+                    for (int u = 0; u < FCHUNK; ++u) {
                         TISPH_CHECK(pA - fL < 2u * LCAP2 + 2u && pB - fL < 2u * LCAP2 + 2u);
-                        filter_rows(xi, yi, zi, ncut, ra[u].x, ra[u].y, ra[u].z, m, pA, pB);
-                        filter_rows(xi, yi, zi, ncut, ra[u].w, rb[u].x, rb[u].y, m + 2u, pA, pB);
+                        filter_rows(xi, yi, zi, T, rec[u], 2u * (uint32_t)(k0 + u), pA, pB);
                     }
                     // a stream that could overflow with the next chunk: the whole item goes to the fallback kernels
                     if (max(pA - fA, pB - fB) > 2u * (LCAP2 - FCHUNK)) { ovf = 1; break; }
@@ -316,7 +324,7 @@ k_density_list(SimParams sp, const int* __restrict__ cell_end, const int2* __res
 #pragma unroll
                 for (uint32_t r8 = 0; r8 < (uint32_t)LCAP2; r8 += 8u) {
                     const uint32_t k = r8 + (uint32_t)j;
-                    if (k < ns && lds_u8(sb + 2u * k) == ms) sts_u8(sb + 2u * k, M_DUMMY + (ms & 1u));
+                    if (k < ns && lds_u8(sb + 2u * k) == (ms & ~1u)) sts_u8(sb + 2u * k, M_DUMMY);
                 }
             }
             __syncwarp();
@@ -328,11 +336,14 @@ k_density_list(SimParams sp, const int* __restrict__ cell_end, const int2* __res
                 const uint32_t ns = a_long ? nA : nB, nd = a_long ? nB : nA;
                 const uint32_t src = sL + (a_long ? offA : offB), dst = sL + (a_long ? offB : offA);
                 const uint32_t mv = min(8u, (ns - nd) >> 1);                // (loads first: their latencies overlap)
+                // even row m in the even stream = entry m - 1 in the odd stream, and back.  Only tail entries move
+                // (at most half of the longer stream, which is ascending): never the entry 0 of an even stream.
+                const uint32_t adj = a_long ? 0xffffffffu : 1u;
                 uint32_t e[8];
 #pragma unroll
                 for (uint32_t u = 0; u < 8u; ++u) if (u < mv) e[u] = lds_u8(src + 2u * (ns - 1u - u));
 #pragma unroll
-                for (uint32_t u = 0; u < 8u; ++u) if (u < mv) sts_u8(dst + 2u * (nd + u), e[u]);
+                for (uint32_t u = 0; u < 8u; ++u) if (u < mv) sts_u8(dst + 2u * (nd + u), e[u] + adj);
                 nA = a_long ? ns - mv : nd + mv;
                 nB = a_long ? nd + mv : ns - mv;
             }
@@ -341,15 +352,15 @@ k_density_list(SimParams sp, const int* __restrict__ cell_end, const int2* __res
             const uint32_t n2 = (2u * max(nA, nB) + 2u) & ~3u;                  // 2 x pairs I hand to the force walk
             const uint32_t nmax = __reduce_max_sync(0xffffffffu, n2);
             for (uint32_t k = 2u * nA; k < nmax; k += 2u) sts_u8(sL + offA + k, M_DUMMY);
-            for (uint32_t k = 2u * nB; k < nmax; k += 2u) sts_u8(sL + offB + k, M_DUMMY + 1);
+            for (uint32_t k = 2u * nB; k < nmax; k += 2u) sts_u8(sL + offB + k, M_DUMMY);       // (row M_DUMMY + 1)
             for (uint32_t k2 = 0; k2 < (sp.lists_only ? 0u : nmax); k2 += 2u) {
                 const uint32_t w = lds_u16(sL + k2);
                 const uint32_t m1 = w & 0xffu, m2 = w >> 8;
                 TISPH_CHECK(k2 < 2u * LCAP2 + 4u && m1 < 256u && m2 < 256u);
-                const float2 xy1 = lds_f32x2(sG + 64u * m1);
-                const float z1 = lds_f32(sGZ + 32u * m1);
-                const float2 xy2 = lds_f32x2(sG + 64u * m2);
-                const float z2 = lds_f32(sGZ + 32u * m2);
+                const float2 xy1 = lds_f32x2(sG1 + 64u * m1);
+                const float z1 = lds_f32(sGZ1 + 32u * m1);
+                const float2 xy2 = lds_f32x2(sG2 + 64u * m2);
+                const float z2 = lds_f32(sGZ2 + 32u * m2);
                 const float2 dx = make_float2(pi.x - xy1.x, pi.x - xy2.x);
                 const float2 dy = make_float2(pi.y - xy1.y, pi.y - xy2.y);
                 const float2 dz = make_float2(pi.z - z1, pi.z - z2);
@@ -374,8 +385,8 @@ k_density_list(SimParams sp, const int* __restrict__ cell_end, const int2* __res
                 if (AKINCI) {
                     const float2 w2 = __ffma2_rn(g3, make_float2(-8.0f, -8.0f), __fmul2_rn(nf3, make_float2(-2.0f, -2.0f)));
                     wsum2 = __fadd2_rn(wsum2, w2);
-                    wbsum += (int)lds_u32(sGM + 32u * m1) == MAT_BOUNDARY ? w2.x : 0.f;
-                    wbsum += (int)lds_u32(sGM + 32u * m2) == MAT_BOUNDARY ? w2.y : 0.f;
+                    wbsum += (int)lds_u32(sGM1 + 32u * m1) == MAT_BOUNDARY ? w2.x : 0.f;
+                    wbsum += (int)lds_u32(sGM2 + 32u * m2) == MAT_BOUNDARY ? w2.y : 0.f;
                 } else {
                     wsum2 = __ffma2_rn(nf3, make_float2(-2.0f, -2.0f), wsum2);
                     wsum2 = __ffma2_rn(g3, make_float2(-8.0f, -8.0f), wsum2);
@@ -519,7 +530,10 @@ k_force_list(SimParams sp, const int* __restrict__ cell_end, const int2* __restr
     const int tid = threadIdx.x;
     const int j = tid & (GL - 1);
     const int n_items = ctr->n_items;
-    const uint32_t sP = smem_u32(P01) + 8u * j, sR = smem_u32(PR) + 4u * j;
+    // first / second entry of a byte pair; the odd stream (second entry of an even group) names the even row of its pair
+    const uint32_t c1 = (tid >> 3) & 1u;
+    const uint32_t sP1 = smem_u32(P01) + 8u * j + 64u * c1, sP2 = smem_u32(P01) + 8u * j + 64u * (1u - c1);
+    const uint32_t sR1 = smem_u32(PR) + 4u * j + 32u * c1, sR2 = smem_u32(PR) + 4u * j + 32u * (1u - c1);
     const float nkdw_h = -sp.k_dw * sp.inv_h;
     if (tid < 16) {                                         // the two dummy rows: FAR away, for good
         const int s = 8 * M_DUMMY + tid;
@@ -613,13 +627,13 @@ k_force_list(SimParams sp, const int* __restrict__ cell_end, const int2* __restr
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     const uint32_t m1 = (cur >> (16 * h)) & 0xffu, m2 = (cur >> (16 * h + 8)) & 0xffu;
-                    const uint32_t a1 = sP + 64u * m1, a2 = sP + 64u * m2;
+                    const uint32_t a1 = sP1 + 64u * m1, a2 = sP2 + 64u * m2;
                     const float2 xy1 = lds_f32x2(a1), zp1 = lds_f32x2(a1 + PLANE_B);
                     const float2 vxy1 = lds_f32x2(a1 + 2u * PLANE_B), vzr1 = lds_f32x2(a1 + 3u * PLANE_B);
-                    const float pr1 = lds_f32(sR + 32u * m1);
+                    const float pr1 = lds_f32(sR1 + 32u * m1);
                     const float2 xy2 = lds_f32x2(a2), zp2 = lds_f32x2(a2 + PLANE_B);
                     const float2 vxy2 = lds_f32x2(a2 + 2u * PLANE_B), vzr2 = lds_f32x2(a2 + 3u * PLANE_B);
-                    const float pr2 = lds_f32(sR + 32u * m2);
+                    const float pr2 = lds_f32(sR2 + 32u * m2);
                     pair_force2<HAS_BOUNDARY>(sp, nkdw_h, pi, vi, coh_kw, rho_i, pr_i, nub_i, xy1, zp1, vxy1, vzr1, pr1,
                                               xy2, zp2, vxy2, vzr2, pr2, A);
                 }
