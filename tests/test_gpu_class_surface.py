@@ -96,10 +96,14 @@ def test_kernel_by_kernel_driver_matches_the_reference_vectors(name, tmp_path):
         assert np.array_equal(np_x, d["position"]) and np.array_equal(np_m, d["material"])
     if name == "gen2_walls":     # the walls moved something in this case, so advert() and the end state differ
         assert not np.array_equal(z["s0.advert.x"], z["s0.end.x"])
-    # the unmodified step() on a second system reaches the same state
+    # the unmodified step() on a second system reaches the same state.  Not bit for bit: driven kernel by kernel the
+    # force walk keeps the non-pressure and the pressure sums apart, the fused step adds both terms of a pair into
+    # one accumulator -- two f32 summation orders of the same terms, each within the tolerance above.
     ps2, solver2 = build(case, z, str(tmp_path))
     solver2.step()
-    assert np.array_equal(ps2.x.to_numpy(), ps.x.to_numpy()) and np.array_equal(ps2.v.to_numpy(), ps.v.to_numpy())
+    assert rel_err(ps2.x.to_numpy(), ps.x.to_numpy(), floor=0.04) < 1e-6
+    assert rel_err(ps2.v.to_numpy(), ps.v.to_numpy(), floor=1.0) < 2 * (RTOL + 2e-4 * scale * RTOL)
+    assert rel_err(ps2.v.to_numpy(), z[f"{t}.end.v"], floor=1.0) < RTOL + 2e-4 * scale * RTOL     # ... and the reference's
     ps.engine.close(); ps2.engine.close()
 
 

@@ -12,9 +12,11 @@ from util import RTOL, check_force_stage, jitter, make_pair, rel_err, small_scen
 pytestmark = pytest.mark.gpu
 
 
-def run_stages(ora, eng, density_mode, p_rtol=RTOL):
+def run_stages(ora, eng, density_mode, p_rtol=RTOL, diagnostics=True):
+    """diagnostics=False is the configuration of a plain step (and of the benchmark): the force walk then adds
+    the non-pressure and the pressure terms of a pair into one accumulator"""
     t = ora.step(trace=True)
-    eng.set_param(K.P_DIAGNOSTICS, 1)
+    eng.set_param(K.P_DIAGNOSTICS, 1 if diagnostics else 0)
     # ---- ps.update(): integer work, bit-exact
     eng.stage(K.STAGE_UPDATE)
     assert np.array_equal(eng.download(K.F_CELL_COUNT), t["counts"])
@@ -39,7 +41,7 @@ def run_stages(ora, eng, density_mode, p_rtol=RTOL):
     # ---- forces + advect + walls: 1e-5 relative to the sum of the magnitudes of the terms each
     #      acceleration adds up (util.accel_err); v' and x' inherit dt and dt^2 times that
     eng.stage(K.STAGE_FORCE_ADVECT)
-    check_force_stage(eng, t, p_rtol=p_rtol)
+    check_force_stage(eng, t, p_rtol=p_rtol, split=diagnostics)
     fl = t["material"] == 1
     assert np.array_equal(eng.download(K.F_MATERIAL), t["material"])
     assert fl.any()
@@ -47,10 +49,11 @@ def run_stages(ora, eng, density_mode, p_rtol=RTOL):
     return t
 
 
+@pytest.mark.parametrize("diagnostics", [True, False], ids=["split-sums", "plain-step"])
 @pytest.mark.parametrize("variant", [0, 1], ids=["lists", "fallback"])
 @pytest.mark.parametrize("density_mode", ["reference", "summed"])
 @pytest.mark.parametrize("state", ["lattice", "jitter"])
-def test_single_step_parity(density_mode, state, variant):
+def test_single_step_parity(density_mode, state, variant, diagnostics):
     """variant 0: packed-f32x2 filter + neighbour lists handed from the density walk to the force
     walk; variant 1: every work item through the self-contained fallback kernels."""
     scene = small_scene()
@@ -61,7 +64,7 @@ def test_single_step_parity(density_mode, state, variant):
         eng0.close()
     ora, eng = make_pair(scene, density_mode=density_mode, x=x)
     eng.set_param(K.P_KERNEL_VARIANT, variant)
-    run_stages(ora, eng, density_mode)
+    run_stages(ora, eng, density_mode, diagnostics=diagnostics)
     eng.close()
 
 

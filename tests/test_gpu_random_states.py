@@ -33,6 +33,17 @@ def random_state(seed, n, domain, h):
 @pytest.mark.parametrize("seed", range(6))
 @pytest.mark.parametrize("dmode,vmode", [("reference", "reference"), ("summed", "akinci"), ("summed", "reference")])
 def test_random_cloud(seed, dmode, vmode):
+    _random_cloud(seed, dmode, vmode, diagnostics=True)
+
+
+@pytest.mark.parametrize("seed", [0, 2, 5])
+@pytest.mark.parametrize("dmode,vmode", [("summed", "akinci"), ("reference", "reference")])
+def test_random_cloud_plain_step(seed, dmode, vmode):
+    """without TISPH_P_DIAGNOSTICS (a plain step): one accumulator for both force sums, boundary neighbours included"""
+    _random_cloud(seed, dmode, vmode, diagnostics=False)
+
+
+def _random_cloud(seed, dmode, vmode, diagnostics):
     scene = small_scene(domain_end=(1.0, 0.8, 0.6))
     h = 0.04
     x, v, density, material = random_state(seed, 6000, (1.0, 0.8, 0.6), h)
@@ -41,7 +52,7 @@ def test_random_cloud(seed, dmode, vmode):
     eng = Engine(sc.gen2_config(scene["configuration"], len(x), density_mode={"reference": 0, "summed": 1}[dmode],
                                 volume_mode={"reference": 0, "akinci": 1}[vmode]))
     eng.add_particles(ora.x, ora.v, ora.density, ora.pressure, ora.material, ora.color)
-    eng.set_param(K.P_DIAGNOSTICS, 1)
+    eng.set_param(K.P_DIAGNOSTICS, 1 if diagnostics else 0)
     t = ora.step(trace=True)
     eng.stage(K.STAGE_UPDATE)
     assert np.array_equal(eng.download(K.F_GRID_PARTICLES_NUM), t["scan"])
@@ -55,7 +66,7 @@ def test_random_cloud(seed, dmode, vmode):
     assert rel_err(eng.download(K.F_VOLUME), t["volume"]) < RTOL
     assert rel_err(eng.download(K.F_DENSITY), t["density"]) < RTOL
     eng.stage(K.STAGE_FORCE_ADVECT)
-    check_force_stage(eng, t)            # 1e-5 relative to the magnitude sums of the terms (util.accel_err)
+    check_force_stage(eng, t, split=diagnostics)      # 1e-5 relative to the magnitude sums of the terms (util.accel_err)
     assert np.array_equal(eng.download(K.F_MATERIAL), t["material"])
     bd = ~fl
     assert np.array_equal(eng.download(K.F_X)[bd], t["x"][bd]) and np.array_equal(eng.download(K.F_V)[bd], t["v"][bd])

@@ -371,7 +371,10 @@ static int run_force(tisph_ctx* c) {
         return TISPH_OK;
     }
     c->walls_pending = c->sp.walls == 0;
-    auto kf = c->has_boundary ? k_force_list<true> : k_force_list<false>;
+    // diagnostics keep the non-pressure and the pressure sums apart (F_A_NONPRESSURE / F_A_PRESSURE); the plain
+    // step needs only their total
+    auto kf = c->has_boundary ? (c->diagnostics ? k_force_list<true, true> : k_force_list<true, false>)
+                              : (c->diagnostics ? k_force_list<false, true> : k_force_list<false, false>);
     kf<<<c->grid_fl, NB_THREADS, FL_SMEM, st>>>(
         c->sp, c->cell_end, c->items, c->ctr, c->P[b], c->V[b], c->Q[b], c->D, c->P[a], c->V[a], c->Q[a],
         c->dvel, dnp, dp, c->Lg, c->item_row, c->item_flags);
@@ -468,8 +471,10 @@ int tisph_create(const tisph_config* cfg, tisph_ctx** out) {
         if (c->nbr_num) A(cudaMemsetAsync(c->nbr_num, 0, cap * 4, c->stream));
         A(cudaFuncSetAttribute(k_density_list<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DL_SMEM));
         A(cudaFuncSetAttribute(k_density_list<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DL_SMEM_AKINCI));
-        A(cudaFuncSetAttribute(k_force_list<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FL_SMEM));
-        A(cudaFuncSetAttribute(k_force_list<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FL_SMEM));
+        A(cudaFuncSetAttribute(k_force_list<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FL_SMEM));
+        A(cudaFuncSetAttribute(k_force_list<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FL_SMEM));
+        A(cudaFuncSetAttribute(k_force_list<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FL_SMEM));
+        A(cudaFuncSetAttribute(k_force_list<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FL_SMEM));
         A(cudaFuncSetAttribute(k_density_fb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DF_SMEM));
         A(cudaFuncSetAttribute(k_force_fb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FF_SMEM));
         int sms = 0, occ = 0;
@@ -481,7 +486,7 @@ int tisph_create(const tisph_config* cfg, tisph_ctx** out) {
         c->arena_rows = c->pool_rows_cap / (4 * c->grid_dl);
         if (c->arena_rows > ARENA_ROWS) c->arena_rows = ARENA_ROWS;
         if (c->arena_rows < 2 * ARENA_MIN) c->arena_rows = 2 * ARENA_MIN;
-        A(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_force_list<true>, NB_THREADS, FL_SMEM));
+        A(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_force_list<true, true>, NB_THREADS, FL_SMEM));
         c->grid_fl = sms * (occ > 0 ? occ : 1);
         c->occ_fl = occ;
         A(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_density_fb, NB_THREADS, DF_SMEM));

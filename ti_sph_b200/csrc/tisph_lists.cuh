@@ -181,6 +181,8 @@ k_density_list(SimParams sp, const int* __restrict__ cell_end, const int2* __res
     const uint32_t sGM1 = smem_u32(GM) + 4u * j + 32u * c1, sGM2 = smem_u32(GM) + 4u * j + 32u * (1u - c1);
     const uint32_t sL = smem_u32(L) + 4u * (LIST_J * j + LIST_T * tD);
     const uint32_t offA = c1, offB = 1u - c1;
+    // the exported words hold TRUE rows: +1 on the bytes of the odd stream (no carry: entries <= 254)
+    const uint32_t odd_plus1 = c1 ? 0x00010001u : 0x01000100u;
     // the two dummy rows are FAR in every array, for good (half: |u| = 1000 makes d2 overflow to +inf)
     if (tid < 16) { GXY[8 * M_DUMMY + tid] = make_float2(FAR, FAR); GZ[8 * M_DUMMY + tid] = FAR; }
     if (AKINCI && tid < 16) GM[8 * M_DUMMY + tid] = MAT_FLUID;
@@ -412,7 +414,7 @@ k_density_list(SimParams sp, const int* __restrict__ cell_end, const int2* __res
                     for (int q4 = 0; q4 < nw; ++q4) {
                         gp += 32;
                         TISPH_CHECK(row + 1 + q4 < pool_rows_cap);
-                        *gp = lds_u32(sL + 4u * q4);
+                        *gp = lds_u32(sL + 4u * q4) + odd_plus1;
                     }
                 }
             }
@@ -453,13 +455,23 @@ constexpr size_t FL_SMEM = (size_t)LT_SLOTS * (4 * sizeof(float2) + sizeof(float
 
 struct ForceAcc2 { float2 anx, any, anz, apx, apy, apz; };
 
+// per-target constants of the pair evaluation.  K = -k_dw: gradW = K gfac0 x_ij with gfac0 = (dW/dq / -6k) / (r h);
+// K is folded into the constants below and, for the pressure sum, applied once in the epilogue.
+struct ForceConst {
+    float c8;            // coh_i k_w W = c8 (g^3 + nf^3 / 4)   (c8 = -8 coh_kw ; wcsphv2.py:64)
+    float cv;            // -nu_fluid K                      (wcsphv2.py:72-73)
+    float cbK, pb, K;    // boundary j: rho0-scaled viscosity coefficient x K ; rho0 p_i/rho_i^2 ; K
+};
+
 // Branch-free evaluation of two neighbours (wcsphv2.py:56-80 ; sph_basev2.py:64-78).  The self pair and
 // coincident particles give exactly zero (x_ij = 0 and gradW = 0 for r <= 1e-5, sph_basev2.py:53);
 // entries outside the cutoff (filter band, list padding) have q clamped to 1, where W and gradW vanish.
 //   dW/dq / (6k) = 4 max(1/2 - q, 0)^2 - (1-q)^2     (sph_basev2.py:53-60)
-template <bool HAS_BOUNDARY>
-__device__ __forceinline__ void pair_force2(const SimParams& sp, float nkdw_h, float4 pi, float4 vi, float coh_kw,
-                                            float rho_i, float pr_i, float nub_i, float2 xy1, float2 zp1, float2 vxy1,
+// SPLIT keeps the non-pressure and the pressure sums apart (diagnostics, kernel-by-kernel stepping); otherwise one
+// accumulator takes  -(non-pressure) + K (pressure)  per pair: three FFMA2 less per two neighbours.
+template <bool HAS_BOUNDARY, bool SPLIT>
+__device__ __forceinline__ void pair_force2(const SimParams& sp, const ForceConst& C, float4 pi, float4 vi,
+                                            float rho_i, float pr_i, float2 xy1, float2 zp1, float2 vxy1,
                                             float2 vzr1, float pr1, float2 xy2, float2 zp2, float2 vxy2, float2 vzr2,
                                             float pr2, ForceAcc2& A) {
     const float2 dx = make_float2(pi.x - xy1.x, pi.x - xy2.x);
@@ -467,17 +479,17 @@ __device__ __forceinline__ void pair_force2(const SimParams& sp, float nkdw_h, f
     const float2 dz = make_float2(pi.z - zp1.x, pi.z - zp2.x);
     const float2 d2 = __ffma2_rn(dz, dz, __ffma2_rn(dy, dy, __fmul2_rn(dx, dx)));
     const float2 rinv = make_float2(rsqrt_approx(fmaxf(d2.x, 1e-30f)), rsqrt_approx(fmaxf(d2.y, 1e-30f)));
-    const float2 r = __fmul2_rn(d2, rinv);
-    float2 q = __fmul2_rn(r, make_float2(sp.inv_h, sp.inv_h));
+    const float2 rih = __fmul2_rn(rinv, make_float2(sp.inv_h, sp.inv_h));           // 1 / (r h)
+    float2 q = __fmul2_rn(d2, rih);
     q.x = fminf(q.x, 1.0f); q.y = fminf(q.y, 1.0f);                  // beyond the support W = gradW = 0: no mask needed
     const float2 nf = __fadd2_rn(q, make_float2(-1.0f, -1.0f));
     float2 g = __ffma2_rn(q, make_float2(-1.0f, -1.0f), make_float2(0.5f, 0.5f));
     g.x = fmaxf(g.x, 0.f); g.y = fmaxf(g.y, 0.f);
     const float2 f2 = __fmul2_rn(nf, nf), g2 = __fmul2_rn(g, g);
     const float2 ndw = __ffma2_rn(g2, make_float2(-4.0f, -4.0f), f2);                 // -dW/dq / (6k)
-    float2 gfac = __fmul2_rn(__fmul2_rn(ndw, rinv), make_float2(nkdw_h, nkdw_h));    // gradW = gfac * x_ij
-    gfac.x = r.x > 1e-5f ? gfac.x : 0.f;
-    gfac.y = r.y > 1e-5f ? gfac.y : 0.f;
+    float2 gfac = __fmul2_rn(ndw, rih);                                               // gradW = K gfac x_ij
+    gfac.x = d2.x > 1e-10f ? gfac.x : 0.f;                                            // r > 1e-5 (sph_basev2.py:53)
+    gfac.y = d2.y > 1e-10f ? gfac.y : 0.f;
     const float2 dvx = make_float2(vi.x - vxy1.x, vi.x - vxy2.x);
     const float2 dvy = make_float2(vi.y - vxy1.y, vi.y - vxy2.y);
     const float2 dvz = make_float2(vi.z - vzr1.x, vi.z - vzr2.x);
@@ -490,27 +502,40 @@ __device__ __forceinline__ void pair_force2(const SimParams& sp, float nkdw_h, f
     const float2 mnr = __fmul2_rn(dot, make_float2(rcp_approx(den.x), rcp_approx(den.y)));
     const float2 t = __fmul2_rn(mnr, gfac);
     const float2 nf3 = __fmul2_rn(f2, nf), g3 = __fmul2_rn(g2, g);
-    // coh_i k_w W/k = coh_kw (-2 nf^3 - 8 g^3)
-    const float2 cw = __fmul2_rn(__ffma2_rn(g3, make_float2(-8.0f, -8.0f), __fmul2_rn(nf3, make_float2(-2.0f, -2.0f))),
-                                 make_float2(coh_kw, coh_kw));
-    const float2 u = __ffma2_rn(t, make_float2(-sp.visc_fluid_c, -sp.visc_fluid_c), cw);   // :64 + :72-73
-    const float2 ps = __fmul2_rn(__fadd2_rn(make_float2(pr1, pr2), make_float2(pr_i, pr_i)), gfac);
-    float2 cn = make_float2(zp1.y * u.x, zp2.y * u.y);                               // psi (coh_i W - nu mn gradW)
-    float2 cp = make_float2(-zp1.y * ps.x, -zp2.y * ps.y);                           // sph_basev2.py:71-73
-    if (HAS_BOUNDARY) {
-        const float2 mnb = __fmul2_rn(t, rs);                                        // min(v.x,0)/(d2+eps) gfac
-        const float cb = sp.ps_density0 * nub_i, pb = sp.rho0 * pr_i;
-        // boundary j: psi = -volume_j                     wcsphv2.py:78-80 ; sph_basev2.py:75
-        cn.x = zp1.y > 0.f ? cn.x : cb * zp1.y * mnb.x;
-        cn.y = zp2.y > 0.f ? cn.y : cb * zp2.y * mnb.y;
-        cp.x = zp1.y > 0.f ? cp.x : pb * zp1.y * gfac.x;
-        cp.y = zp2.y > 0.f ? cp.y : pb * zp2.y * gfac.y;
+    const float2 ps = __fmul2_rn(__fadd2_rn(make_float2(pr1, pr2), make_float2(pr_i, pr_i)), gfac);   // sph_basev2.py:71-73 (/ K)
+    if (SPLIT) {
+        const float2 cw = __fmul2_rn(__ffma2_rn(nf3, make_float2(0.25f, 0.25f), g3), make_float2(C.c8, C.c8));
+        const float2 u = __ffma2_rn(t, make_float2(C.cv, C.cv), cw);                  // :64 + :72-73
+        float2 cn = make_float2(zp1.y * u.x, zp2.y * u.y);                            // psi (coh_i W - nu mn gradW)
+        float2 cp = make_float2(-zp1.y * ps.x, -zp2.y * ps.y);
+        if (HAS_BOUNDARY) {
+            const float2 mnb = __fmul2_rn(t, rs);                                     // min(v.x,0)/(d2+eps) gfac
+            // boundary j: psi = -volume_j                     wcsphv2.py:78-80 ; sph_basev2.py:75
+            cn.x = zp1.y > 0.f ? cn.x : C.cbK * zp1.y * mnb.x;
+            cn.y = zp2.y > 0.f ? cn.y : C.cbK * zp2.y * mnb.y;
+            cp.x = zp1.y > 0.f ? cp.x : C.pb * zp1.y * gfac.x;
+            cp.y = zp2.y > 0.f ? cp.y : C.pb * zp2.y * gfac.y;
+        }
+        A.anx = __ffma2_rn(cn, dx, A.anx); A.any = __ffma2_rn(cn, dy, A.any); A.anz = __ffma2_rn(cn, dz, A.anz);
+        A.apx = __ffma2_rn(cp, dx, A.apx); A.apy = __ffma2_rn(cp, dy, A.apy); A.apz = __ffma2_rn(cp, dz, A.apz);
+    } else {
+        // w = -(coh_i W - nu mn gradW) - K (p_i/rho_i^2 + p_j/rho_j^2) gfac ;  a_i += psi w x_ij
+        const float2 cwn = __fmul2_rn(__ffma2_rn(nf3, make_float2(0.25f, 0.25f), g3), make_float2(-C.c8, -C.c8));
+        const float2 un = __ffma2_rn(t, make_float2(-C.cv, -C.cv), cwn);
+        float2 w = __ffma2_rn(ps, make_float2(-C.K, -C.K), un);
+        if (HAS_BOUNDARY) {
+            const float2 mnb = __fmul2_rn(t, rs);
+            const float pbK = C.pb * C.K;
+            const float2 wb = __ffma2_rn(mnb, make_float2(-C.cbK, -C.cbK), __fmul2_rn(gfac, make_float2(pbK, pbK)));
+            w.x = zp1.y > 0.f ? w.x : wb.x;
+            w.y = zp2.y > 0.f ? w.y : wb.y;
+        }
+        const float2 c = make_float2(zp1.y * w.x, zp2.y * w.y);
+        A.anx = __ffma2_rn(c, dx, A.anx); A.any = __ffma2_rn(c, dy, A.any); A.anz = __ffma2_rn(c, dz, A.anz);
     }
-    A.anx = __ffma2_rn(cn, dx, A.anx); A.any = __ffma2_rn(cn, dy, A.any); A.anz = __ffma2_rn(cn, dz, A.anz);
-    A.apx = __ffma2_rn(cp, dx, A.apx); A.apy = __ffma2_rn(cp, dy, A.apy); A.apz = __ffma2_rn(cp, dz, A.apz);
 }
 
-template <bool HAS_BOUNDARY>
+template <bool HAS_BOUNDARY, bool SPLIT>
 __global__ void __launch_bounds__(NB_THREADS, 3)
 k_force_list(SimParams sp, const int* __restrict__ cell_end, const int2* __restrict__ items,
              StepCounters* __restrict__ ctr, const float4* __restrict__ Pin,
@@ -530,11 +555,7 @@ k_force_list(SimParams sp, const int* __restrict__ cell_end, const int2* __restr
     const int tid = threadIdx.x;
     const int j = tid & (GL - 1);
     const int n_items = ctr->n_items;
-    // first / second entry of a byte pair; the odd stream (second entry of an even group) names the even row of its pair
-    const uint32_t c1 = (tid >> 3) & 1u;
-    const uint32_t sP1 = smem_u32(P01) + 8u * j + 64u * c1, sP2 = smem_u32(P01) + 8u * j + 64u * (1u - c1);
-    const uint32_t sR1 = smem_u32(PR) + 4u * j + 32u * c1, sR2 = smem_u32(PR) + 4u * j + 32u * (1u - c1);
-    const float nkdw_h = -sp.k_dw * sp.inv_h;
+    const uint32_t sP = smem_u32(P01) + 8u * j, sR = smem_u32(PR) + 4u * j;
     if (tid < 16) {                                         // the two dummy rows: FAR away, for good
         const int s = 8 * M_DUMMY + tid;
         P01[s] = make_float2(FAR, FAR); P23[s] = make_float2(FAR, 1.f);
@@ -610,6 +631,12 @@ k_force_list(SimParams sp, const int* __restrict__ cell_end, const int2* __restr
             const float coh_kw = 0.01f / pi.w * sp.k_w;                // wcsphv2.py:64 (x the kernel normalisation)
             const float rho_i = di.x, pr_i = di.y;
             const float nub_i = sp.visc_bound_c / (2.0f * rho_i);     // wcsphv2.py:76
+            ForceConst C;
+            C.K = -sp.k_dw;
+            C.c8 = -8.0f * coh_kw;
+            C.cv = -sp.visc_fluid_c * C.K;
+            C.cbK = sp.ps_density0 * nub_i * C.K;                     // wcsphv2.py:78-80
+            C.pb = sp.rho0 * pr_i;                                    // sph_basev2.py:75
             ForceAcc2 A;
             A.anx = A.any = A.anz = A.apx = A.apy = A.apz = make_float2(0.f, 0.f);
             const int row = pass ? row_p1 : row_p0;
@@ -627,15 +654,15 @@ k_force_list(SimParams sp, const int* __restrict__ cell_end, const int2* __restr
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     const uint32_t m1 = (cur >> (16 * h)) & 0xffu, m2 = (cur >> (16 * h + 8)) & 0xffu;
-                    const uint32_t a1 = sP1 + 64u * m1, a2 = sP2 + 64u * m2;
+                    const uint32_t a1 = sP + 64u * m1, a2 = sP + 64u * m2;
                     const float2 xy1 = lds_f32x2(a1), zp1 = lds_f32x2(a1 + PLANE_B);
                     const float2 vxy1 = lds_f32x2(a1 + 2u * PLANE_B), vzr1 = lds_f32x2(a1 + 3u * PLANE_B);
-                    const float pr1 = lds_f32(sR1 + 32u * m1);
+                    const float pr1 = lds_f32(sR + 32u * m1);
                     const float2 xy2 = lds_f32x2(a2), zp2 = lds_f32x2(a2 + PLANE_B);
                     const float2 vxy2 = lds_f32x2(a2 + 2u * PLANE_B), vzr2 = lds_f32x2(a2 + 3u * PLANE_B);
-                    const float pr2 = lds_f32(sR2 + 32u * m2);
-                    pair_force2<HAS_BOUNDARY>(sp, nkdw_h, pi, vi, coh_kw, rho_i, pr_i, nub_i, xy1, zp1, vxy1, vzr1, pr1,
-                                              xy2, zp2, vxy2, vzr2, pr2, A);
+                    const float pr2 = lds_f32(sR + 32u * m2);
+                    pair_force2<HAS_BOUNDARY, SPLIT>(sp, C, pi, vi, rho_i, pr_i, xy1, zp1, vxy1, vzr1, pr1,
+                                                     xy2, zp2, vxy2, vzr2, pr2, A);
                 }
             }
             float a6[6] = {A.anx.x + A.anx.y, A.any.x + A.any.y, A.anz.x + A.anz.y,
@@ -643,10 +670,15 @@ k_force_list(SimParams sp, const int* __restrict__ cell_end, const int2* __restr
 #pragma unroll
             for (int o = 1; o < GL; o <<= 1)
 #pragma unroll
-                for (int c = 0; c < 6; ++c) a6[c] += __shfl_xor_sync(0xffffffffu, a6[c], o);
-            if (j == 0 && active)
-                force_epilogue(sp, i, walker, pi, vi, di, qi, a6[0], a6[1], a6[2], a6[3], a6[4], a6[5],
-                               Pout, Vout, Qout, dvel, a_np_out, a_p_out);
+                for (int c = 0; c < (SPLIT ? 6 : 3); ++c) a6[c] += __shfl_xor_sync(0xffffffffu, a6[c], o);
+            if (j == 0 && active) {
+                if (SPLIT)      // a = g - (non-pressure sum) + K (pressure sum)
+                    force_epilogue(sp, i, walker, pi, vi, di, qi, a6[0], a6[1], a6[2], C.K * a6[3], C.K * a6[4], C.K * a6[5],
+                                   Pout, Vout, Qout, dvel, a_np_out, a_p_out);
+                else            // a = g + (the one sum)
+                    force_epilogue(sp, i, walker, pi, vi, di, qi, -a6[0], -a6[1], -a6[2], 0.f, 0.f, 0.f,
+                                   Pout, Vout, Qout, dvel, nullptr, nullptr);
+            }
         }
         // the one barrier between two items: the next item's ranges go to the other buffer, which nobody reads now
         if (tid < 32) publish_item(nx, R2[buf ^ 1], M2[buf ^ 1]);
