@@ -126,13 +126,16 @@ def test_subclass_hooks_are_called_in_the_reference_order():
         probe.step()
         stock.step()
     assert calls == ["substep", "enforce_boundary"] * 2
-    assert np.array_equal(ps.x.to_numpy(), ps_ref.x.to_numpy()) and np.array_equal(ps.v.to_numpy(), ps_ref.v.to_numpy())
+    # (same terms, two f32 summation orders: the hooked solver runs kernel by kernel with the force sums kept apart,
+    #  the stock one fused with one accumulator -- hence a tolerance, not bit equality)
+    assert rel_err(ps.x.to_numpy(), ps_ref.x.to_numpy(), floor=0.04) < 1e-6
+    assert rel_err(ps.v.to_numpy(), ps_ref.v.to_numpy(), floor=1.0) < 4 * RTOL
     # ps.update() by the script, then solver.step(): the step continues from the sorted state
     ps.update()
     probe.step()
     ps_ref.update()
     stock.step()
-    assert np.array_equal(ps.x.to_numpy(), ps_ref.x.to_numpy())
+    assert rel_err(ps.x.to_numpy(), ps_ref.x.to_numpy(), floor=0.04) < 1e-6
     ps.engine.close(); ps_ref.engine.close()
 
 

@@ -130,17 +130,35 @@ constexpr size_t DL_SMEM_AKINCI = DL_SMEM + (size_t)LT_SLOTS * sizeof(int);
 __device__ __forceinline__ uint32_t h2_bits(__half2 v) { return *reinterpret_cast<uint32_t*>(&v); }
 __device__ __forceinline__ __half2 bits_h2(uint32_t v) { return *reinterpret_cast<__half2*>(&v); }
 
-// one row pair of the filter: s = n_j - 2 u_i.u_j for the two rows (xi, yi, zi hold -2 u_i; s < T = survivor),
-// then the predicated pushes of the pair's EVEN row byte m to the two pending streams
-__device__ __forceinline__ void filter_rows(__half2 xi, __half2 yi, __half2 zi, uint32_t T, uint4 rec, uint32_t m,
-                                            uint32_t& pA, uint32_t& pB) {
-    const __half2 s = __hfma2(xi, bits_h2(rec.x), __hfma2(yi, bits_h2(rec.y), __hfma2(zi, bits_h2(rec.z), bits_h2(rec.w))));
-    asm volatile("{\n\t.reg .pred p, q;\n\t"
-                 "setp.lt.f16x2 p|q, %2, %3;\n\t"
-                 "@p st.shared.u8 [%0], %4;\n\t@p add.u32 %0, %0, 2;\n\t"
-                 "@q st.shared.u8 [%1], %4;\n\t@q add.u32 %1, %1, 2;\n\t}"
-                 : "+r"(pA), "+r"(pB) : "r"(h2_bits(s)), "r"(T), "r"(m) : "memory");
+// one row pair of the filter: s = n_j - 2 u_i.u_j for the two rows (xi, yi, zi hold -2 u_i; s < T = survivor)
+__device__ __forceinline__ uint32_t filter_rows(__half2 xi, __half2 yi, __half2 zi, uint4 rec) {
+    return h2_bits(__hfma2(xi, bits_h2(rec.x), __hfma2(yi, bits_h2(rec.y), __hfma2(zi, bits_h2(rec.z), bits_h2(rec.w)))));
 }
+// ... and the predicated pushes of FCHUNK = 8 row pairs: the EVEN row byte m0 + 2u of pair u goes to the pending
+// stream of each of its two rows that survived (one asm block: the stream pointers stay in their registers)
+__device__ __forceinline__ void filter_push8(uint32_t& pA, uint32_t& pB, const uint32_t (&sv)[8], uint32_t T, uint32_t m0) {
+    asm volatile("{\n\t.reg .pred p, q;\n\t.reg .b32 m;\n\t"
+                 "setp.lt.f16x2 p|q, %2, %10;\n\t"
+                 "@p st.shared.u8 [%0], %11;\n\t@p add.u32 %0, %0, 2;\n\t@q st.shared.u8 [%1], %11;\n\t@q add.u32 %1, %1, 2;\n\t"
+                 "setp.lt.f16x2 p|q, %3, %10;\n\tadd.u32 m, %11, 2;\n\t"
+                 "@p st.shared.u8 [%0], m;\n\t@p add.u32 %0, %0, 2;\n\t@q st.shared.u8 [%1], m;\n\t@q add.u32 %1, %1, 2;\n\t"
+                 "setp.lt.f16x2 p|q, %4, %10;\n\tadd.u32 m, %11, 4;\n\t"
+                 "@p st.shared.u8 [%0], m;\n\t@p add.u32 %0, %0, 2;\n\t@q st.shared.u8 [%1], m;\n\t@q add.u32 %1, %1, 2;\n\t"
+                 "setp.lt.f16x2 p|q, %5, %10;\n\tadd.u32 m, %11, 6;\n\t"
+                 "@p st.shared.u8 [%0], m;\n\t@p add.u32 %0, %0, 2;\n\t@q st.shared.u8 [%1], m;\n\t@q add.u32 %1, %1, 2;\n\t"
+                 "setp.lt.f16x2 p|q, %6, %10;\n\tadd.u32 m, %11, 8;\n\t"
+                 "@p st.shared.u8 [%0], m;\n\t@p add.u32 %0, %0, 2;\n\t@q st.shared.u8 [%1], m;\n\t@q add.u32 %1, %1, 2;\n\t"
+                 "setp.lt.f16x2 p|q, %7, %10;\n\tadd.u32 m, %11, 10;\n\t"
+                 "@p st.shared.u8 [%0], m;\n\t@p add.u32 %0, %0, 2;\n\t@q st.shared.u8 [%1], m;\n\t@q add.u32 %1, %1, 2;\n\t"
+                 "setp.lt.f16x2 p|q, %8, %10;\n\tadd.u32 m, %11, 12;\n\t"
+                 "@p st.shared.u8 [%0], m;\n\t@p add.u32 %0, %0, 2;\n\t@q st.shared.u8 [%1], m;\n\t@q add.u32 %1, %1, 2;\n\t"
+                 "setp.lt.f16x2 p|q, %9, %10;\n\tadd.u32 m, %11, 14;\n\t"
+                 "@p st.shared.u8 [%0], m;\n\t@p add.u32 %0, %0, 2;\n\t@q st.shared.u8 [%1], m;\n\t@q add.u32 %1, %1, 2;\n\t}"
+                 : "+r"(pA), "+r"(pB)
+                 : "r"(sv[0]), "r"(sv[1]), "r"(sv[2]), "r"(sv[3]), "r"(sv[4]), "r"(sv[5]), "r"(sv[6]), "r"(sv[7]), "r"(T), "r"(m0)
+                 : "memory");
+}
+static_assert(FCHUNK == 8, "filter_push8 is written for chunks of 8 row pairs");
 
 template <bool AKINCI>
 __global__ void __launch_bounds__(NB_THREADS, 3)
@@ -294,11 +312,11 @@ k_density_list(SimParams sp, const int* __restrict__ cell_end, const int2* __res
                     for (int u = 0; u < FCHUNK; ++u)
                         asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(rec[u].x), "=r"(rec[u].y), "=r"(rec[u].z), "=r"(rec[u].w)
                                      : "r"(fT + 128u * (uint32_t)(k0 + u)) : "memory");
+                    uint32_t sv[FCHUNK];
 #pragma unroll
-                    for (int u = 0; u < FCHUNK; ++u) {
-                        TISPH_CHECK(pA - fL < 2u * LCAP2 + 2u && pB - fL < 2u * LCAP2 + 2u);
-                        filter_rows(xi, yi, zi, T, rec[u], 2u * (uint32_t)(k0 + u), pA, pB);
-                    }
+                    for (int u = 0; u < FCHUNK; ++u) sv[u] = filter_rows(xi, yi, zi, rec[u]);
+                    TISPH_CHECK(pA - fL < 2u * LCAP2 + 2u && pB - fL < 2u * LCAP2 + 2u);
+                    filter_push8(pA, pB, sv, T, 2u * (uint32_t)k0);
                     // a stream that could overflow with the next chunk: the whole item goes to the fallback kernels
                     if (max(pA - fA, pB - fB) > 2u * (LCAP2 - FCHUNK)) { ovf = 1; break; }
                 }
@@ -373,10 +391,12 @@ k_density_list(SimParams sp, const int* __restrict__ cell_end, const int2* __res
                 const float2 rinv = make_float2(rsqrt_approx(fmaxf(d2.x, 1e-30f)), rsqrt_approx(fmaxf(d2.y, 1e-30f)));
                 // r = d2 / sqrt(d2) with one Newton step on top of MUFU.RSQ: the density sum feeds p = B (x^7 - 1),
                 // which multiplies its relative error by 7 and more, so r is kept to ~1 ulp here
+                // (in units of h: q0 = d2 rinv / h, e = q0 (rinv h) - 1... written on r0 = d2 rinv: e = r0 rinv - 1 = -err,
+                //  q = (r0 - r0/2 e) / h, with r0 / h and -r0 / 2h as the two products)
                 const float2 r0 = __fmul2_rn(d2, rinv);
-                const float2 e = __ffma2_rn(__fmul2_rn(r0, make_float2(-1.0f, -1.0f)), rinv, make_float2(1.0f, 1.0f));
-                const float2 r = __ffma2_rn(__fmul2_rn(r0, make_float2(0.5f, 0.5f)), e, r0);
-                float2 q = __fmul2_rn(r, make_float2(sp.inv_h, sp.inv_h));
+                const float2 e = __ffma2_rn(r0, rinv, make_float2(-1.0f, -1.0f));
+                const float2 q0 = __fmul2_rn(r0, make_float2(sp.inv_h, sp.inv_h));
+                float2 q = __ffma2_rn(__fmul2_rn(q0, make_float2(-0.5f, -0.5f)), e, q0);
                 q.x = fminf(q.x, 1.0f); q.y = fminf(q.y, 1.0f);
                 // cubic spline, branch-free:  W/k = 2 (1-q)^3 - 8 max(1/2 - q, 0)^3   (sph_basev2.py:19-36)
                 const float2 nf = __fadd2_rn(q, make_float2(-1.0f, -1.0f));
@@ -461,6 +481,7 @@ struct ForceConst {
     float c8;            // coh_i k_w W = c8 (g^3 + nf^3 / 4)   (c8 = -8 coh_kw ; wcsphv2.py:64)
     float cv;            // -nu_fluid K                      (wcsphv2.py:72-73)
     float cbK, pb, K;    // boundary j: rho0-scaled viscosity coefficient x K ; rho0 p_i/rho_i^2 ; K
+    float nKpi;          // -K p_i / rho_i^2
 };
 
 // Branch-free evaluation of two neighbours (wcsphv2.py:56-80 ; sph_basev2.py:64-78).  The self pair and
@@ -500,10 +521,10 @@ __device__ __forceinline__ void pair_force2(const SimParams& sp, const ForceCons
     const float2 rs = make_float2(rho_i + vzr1.y, rho_i + vzr2.y);
     const float2 den = __fmul2_rn(d2e, rs);
     const float2 mnr = __fmul2_rn(dot, make_float2(rcp_approx(den.x), rcp_approx(den.y)));
-    const float2 t = __fmul2_rn(mnr, gfac);
     const float2 nf3 = __fmul2_rn(f2, nf), g3 = __fmul2_rn(g2, g);
-    const float2 ps = __fmul2_rn(__fadd2_rn(make_float2(pr1, pr2), make_float2(pr_i, pr_i)), gfac);   // sph_basev2.py:71-73 (/ K)
     if (SPLIT) {
+        const float2 t = __fmul2_rn(mnr, gfac);
+        const float2 ps = __fmul2_rn(__fadd2_rn(make_float2(pr1, pr2), make_float2(pr_i, pr_i)), gfac);   // sph_basev2.py:71-73 (/ K)
         const float2 cw = __fmul2_rn(__ffma2_rn(nf3, make_float2(0.25f, 0.25f), g3), make_float2(C.c8, C.c8));
         const float2 u = __ffma2_rn(t, make_float2(C.cv, C.cv), cw);                  // :64 + :72-73
         float2 cn = make_float2(zp1.y * u.x, zp2.y * u.y);                            // psi (coh_i W - nu mn gradW)
@@ -519,17 +540,19 @@ __device__ __forceinline__ void pair_force2(const SimParams& sp, const ForceCons
         A.anx = __ffma2_rn(cn, dx, A.anx); A.any = __ffma2_rn(cn, dy, A.any); A.anz = __ffma2_rn(cn, dz, A.anz);
         A.apx = __ffma2_rn(cp, dx, A.apx); A.apy = __ffma2_rn(cp, dy, A.apy); A.apz = __ffma2_rn(cp, dz, A.apz);
     } else {
-        // w = -(coh_i W - nu mn gradW) - K (p_i/rho_i^2 + p_j/rho_j^2) gfac ;  a_i += psi w x_ij
-        const float2 cwn = __fmul2_rn(__ffma2_rn(nf3, make_float2(0.25f, 0.25f), g3), make_float2(-C.c8, -C.c8));
-        const float2 un = __ffma2_rn(t, make_float2(-C.cv, -C.cv), cwn);
-        float2 w = __ffma2_rn(ps, make_float2(-C.K, -C.K), un);
+        // a_i += psi w x_ij,  w = -(coh_i W - nu mn gradW) - K (p_i/rho_i^2 + p_j/rho_j^2) gfac
+        //                       = gfac (-K p_j/rho_j^2 - K p_i/rho_i^2 + nu K mn) - coh_i W
+        float2 cwn = __fmul2_rn(__ffma2_rn(nf3, make_float2(0.25f, 0.25f), g3), make_float2(-C.c8, -C.c8));
+        float2 in = __ffma2_rn(mnr, make_float2(-C.cv, -C.cv),
+                               __ffma2_rn(make_float2(pr1, pr2), make_float2(-C.K, -C.K), make_float2(C.nKpi, C.nKpi)));
         if (HAS_BOUNDARY) {
-            const float2 mnb = __fmul2_rn(t, rs);
+            // boundary j: w = gfac (K rho0 p_i/rho_i^2 - cbK mn (rho_i + rho_j)), no cohesion   wcsphv2.py:78-80 ; sph_basev2.py:75
             const float pbK = C.pb * C.K;
-            const float2 wb = __ffma2_rn(mnb, make_float2(-C.cbK, -C.cbK), __fmul2_rn(gfac, make_float2(pbK, pbK)));
-            w.x = zp1.y > 0.f ? w.x : wb.x;
-            w.y = zp2.y > 0.f ? w.y : wb.y;
+            const float2 inb = __ffma2_rn(__fmul2_rn(mnr, rs), make_float2(-C.cbK, -C.cbK), make_float2(pbK, pbK));
+            in.x = zp1.y > 0.f ? in.x : inb.x;   cwn.x = zp1.y > 0.f ? cwn.x : 0.f;
+            in.y = zp2.y > 0.f ? in.y : inb.y;   cwn.y = zp2.y > 0.f ? cwn.y : 0.f;
         }
+        const float2 w = __ffma2_rn(gfac, in, cwn);
         const float2 c = make_float2(zp1.y * w.x, zp2.y * w.y);
         A.anx = __ffma2_rn(c, dx, A.anx); A.any = __ffma2_rn(c, dy, A.any); A.anz = __ffma2_rn(c, dz, A.anz);
     }
@@ -637,6 +660,7 @@ k_force_list(SimParams sp, const int* __restrict__ cell_end, const int2* __restr
             C.cv = -sp.visc_fluid_c * C.K;
             C.cbK = sp.ps_density0 * nub_i * C.K;                     // wcsphv2.py:78-80
             C.pb = sp.rho0 * pr_i;                                    // sph_basev2.py:75
+            C.nKpi = -C.K * pr_i;
             ForceAcc2 A;
             A.anx = A.any = A.anz = A.apx = A.apy = A.apz = make_float2(0.f, 0.f);
             const int row = pass ? row_p1 : row_p0;
