@@ -73,12 +73,27 @@ __device__ __forceinline__ int slot_to_cand(int s) {
 __device__ __forceinline__ void sts_u8(uint32_t a, uint32_t v) {
     asm volatile("st.shared.u8 [%0], %1;" :: "r"(a), "r"(v) : "memory");
 }
+__device__ __forceinline__ void cp_async8(uint32_t dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async4(uint32_t dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void prefetch_l2(const void* p) {
     asm volatile("prefetch.global.L2 [%0];" :: "l"(p));
 }
 __device__ __forceinline__ uint32_t lds_u8(uint32_t a) {
     uint32_t v;
     asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    return v;
+}
+// byte K of a word, zero-extended (one PRMT)
+template <int K>
+__device__ __forceinline__ uint32_t byte_of(uint32_t w) {
+    uint32_t v;
+    asm("prmt.b32 %0, %1, 0, %2;" : "=r"(v) : "r"(w), "n"(0x4440 + K));
     return v;
 }
 __device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
@@ -373,14 +388,14 @@ k_density_list(SimParams sp, const int* __restrict__ cell_end, const int2* __res
             const uint32_t nmax = __reduce_max_sync(0xffffffffu, n2);
             for (uint32_t k = 2u * nA; k < nmax; k += 2u) sts_u8(sL + offA + k, M_DUMMY);
             for (uint32_t k = 2u * nB; k < nmax; k += 2u) sts_u8(sL + offB + k, M_DUMMY);       // (row M_DUMMY + 1)
-            for (uint32_t k2 = 0; k2 < (sp.lists_only ? 0u : nmax); k2 += 2u) {
-                const uint32_t w = lds_u16(sL + k2);
-                const uint32_t m1 = w & 0xffu, m2 = w >> 8;
-                TISPH_CHECK(k2 < 2u * LCAP2 + 4u && m1 < 256u && m2 < 256u);
-                const float2 xy1 = lds_f32x2(sG1 + 64u * m1);
-                const float z1 = lds_f32(sGZ1 + 32u * m1);
-                const float2 xy2 = lds_f32x2(sG2 + 64u * m2);
-                const float z2 = lds_f32(sGZ2 + 32u * m2);
+            // one word = two (first, second) pairs of entries; a byte is taken out with one PRMT and scaled into its
+            // plane address by one shift-add each
+            auto drain2 = [&](uint32_t m1, uint32_t m2) {
+                TISPH_CHECK(m1 < 256u && m2 < 256u);
+                const float2 xy1 = lds_f32x2(sG1 + (m1 << 6));
+                const float z1 = lds_f32(sGZ1 + (m1 << 5));
+                const float2 xy2 = lds_f32x2(sG2 + (m2 << 6));
+                const float z2 = lds_f32(sGZ2 + (m2 << 5));
                 const float2 dx = make_float2(pi.x - xy1.x, pi.x - xy2.x);
                 const float2 dy = make_float2(pi.y - xy1.y, pi.y - xy2.y);
                 const float2 dz = make_float2(pi.z - z1, pi.z - z2);
@@ -389,10 +404,9 @@ k_density_list(SimParams sp, const int* __restrict__ cell_end, const int2* __res
                 // sums are written as fma(y2, 1, x2) with a run-time 1: exact, and nothing left to contract.
                 const float2 d2 = __ffma2_rn(__fmul2_rn(dz, dz), one2, __ffma2_rn(__fmul2_rn(dy, dy), one2, __fmul2_rn(dx, dx)));
                 const float2 rinv = make_float2(rsqrt_approx(fmaxf(d2.x, 1e-30f)), rsqrt_approx(fmaxf(d2.y, 1e-30f)));
-                // r = d2 / sqrt(d2) with one Newton step on top of MUFU.RSQ: the density sum feeds p = B (x^7 - 1),
-                // which multiplies its relative error by 7 and more, so r is kept to ~1 ulp here
-                // (in units of h: q0 = d2 rinv / h, e = q0 (rinv h) - 1... written on r0 = d2 rinv: e = r0 rinv - 1 = -err,
-                //  q = (r0 - r0/2 e) / h, with r0 / h and -r0 / 2h as the two products)
+                // q = sqrt(d2) / h with one Newton step on top of MUFU.RSQ: the density sum feeds p = B (x^7 - 1),
+                // which multiplies its relative error by 7 and more, so q is kept to ~1 ulp here:
+                // r0 = d2 rinv, e = r0 rinv - 1, q = r0/h - (r0/2h) e
                 const float2 r0 = __fmul2_rn(d2, rinv);
                 const float2 e = __ffma2_rn(r0, rinv, make_float2(-1.0f, -1.0f));
                 const float2 q0 = __fmul2_rn(r0, make_float2(sp.inv_h, sp.inv_h));
@@ -400,21 +414,26 @@ k_density_list(SimParams sp, const int* __restrict__ cell_end, const int2* __res
                 q.x = fminf(q.x, 1.0f); q.y = fminf(q.y, 1.0f);
                 // cubic spline, branch-free:  W/k = 2 (1-q)^3 - 8 max(1/2 - q, 0)^3   (sph_basev2.py:19-36)
                 const float2 nf = __fadd2_rn(q, make_float2(-1.0f, -1.0f));
-                float2 g = __ffma2_rn(q, make_float2(-1.0f, -1.0f), make_float2(0.5f, 0.5f));
-                g.x = fmaxf(g.x, 0.f); g.y = fmaxf(g.y, 0.f);
+                float2 g = make_float2(fmaxf(-0.5f - nf.x, 0.f), fmaxf(-0.5f - nf.y, 0.f));
                 const float2 nf3 = __fmul2_rn(__fmul2_rn(nf, nf), nf);
                 const float2 g3 = __fmul2_rn(__fmul2_rn(g, g), g);
                 if (AKINCI) {
                     const float2 w2 = __ffma2_rn(g3, make_float2(-8.0f, -8.0f), __fmul2_rn(nf3, make_float2(-2.0f, -2.0f)));
                     wsum2 = __fadd2_rn(wsum2, w2);
-                    wbsum += (int)lds_u32(sGM1 + 32u * m1) == MAT_BOUNDARY ? w2.x : 0.f;
-                    wbsum += (int)lds_u32(sGM2 + 32u * m2) == MAT_BOUNDARY ? w2.y : 0.f;
+                    wbsum += (int)lds_u32(sGM1 + (m1 << 5)) == MAT_BOUNDARY ? w2.x : 0.f;
+                    wbsum += (int)lds_u32(sGM2 + (m2 << 5)) == MAT_BOUNDARY ? w2.y : 0.f;
                 } else {
                     wsum2 = __ffma2_rn(nf3, make_float2(-2.0f, -2.0f), wsum2);
                     wsum2 = __ffma2_rn(g3, make_float2(-8.0f, -8.0f), wsum2);
                 }
-                if (d2.x < sp.d2_cut) ++cnt;
-                if (d2.y < sp.d2_cut) ++cnt;
+                asm("{\n\t.reg .pred p, q;\n\tsetp.lt.f32 p, %1, %3;\n\tsetp.lt.f32 q, %2, %3;\n\t"
+                    "@p add.s32 %0, %0, 1;\n\t@q add.s32 %0, %0, 1;\n\t}" : "+r"(cnt) : "f"(d2.x), "f"(d2.y), "f"(sp.d2_cut));
+            };
+            for (uint32_t k4 = 0; k4 < (sp.lists_only ? 0u : nmax); k4 += 4u) {
+                const uint32_t w = lds_u32(sL + k4);
+                TISPH_CHECK(k4 < 2u * LCAP2 + 4u);
+                drain2(byte_of<0>(w), byte_of<1>(w));
+                drain2(byte_of<2>(w), byte_of<3>(w));
             }
             // ---- hand my pairs to the force walk: the warp reserves a count row and the rows of its longest
             //      lane (rows of 32 words), then copies whole words of (first, second, first, second) entries
@@ -467,7 +486,10 @@ k_density_list(SimParams sp, const int* __restrict__ cell_end, const int2* __res
 
 // =======================================================================================
 // Walk 2: forces + advect + walls.  Tile = five planes of LT_SLOTS 8-byte (4-byte) slots:
-//   P01 {x,y}   P23 {z,psi}   V01 {vx,vy}   V23 {vz,rho_raw}   PR p/rho_c^2
+//   P01 {x,y}   P23 {z,psi}   V01 {vx,vy}   RP {rho_raw, p/rho_c^2}   VZ vz
+// every plane is a contiguous piece of one source record (P.xy, {P.z, D.z}, V.xy, D.xy, V.z), so the tile is staged
+// with asynchronous global -> shared copies (cp.async: no registers in between, all of a thread's copies in flight
+// at once)
 //   psi = +mass_j (fluid j) / -volume_j (boundary j)
 // =======================================================================================
 constexpr uint32_t PLANE_B = (uint32_t)LT_SLOTS * sizeof(float2);
@@ -571,19 +593,20 @@ k_force_list(SimParams sp, const int* __restrict__ cell_end, const int2* __restr
     float2* P01 = reinterpret_cast<float2*>(dyn_smem);
     float2* P23 = P01 + LT_SLOTS;
     float2* V01 = P23 + LT_SLOTS;
-    float2* V23 = V01 + LT_SLOTS;
-    float* PR = reinterpret_cast<float*>(V23 + LT_SLOTS);
+    float2* RP = V01 + LT_SLOTS;
+    float* VZ = reinterpret_cast<float*>(RP + LT_SLOTS);
     __shared__ CellRanges R2[2];                     // current item / the one being published
     __shared__ ItemMeta M2[2];
     const int tid = threadIdx.x;
     const int j = tid & (GL - 1);
     const int n_items = ctr->n_items;
-    const uint32_t sP = smem_u32(P01) + 8u * j, sR = smem_u32(PR) + 4u * j;
+    const uint32_t sP = smem_u32(P01) + 8u * j, sVZ = smem_u32(VZ) + 4u * j;
+    const uint32_t tP01 = smem_u32(P01), tVZ = smem_u32(VZ);
     if (tid < 16) {                                         // the two dummy rows: FAR away, for good
         const int s = 8 * M_DUMMY + tid;
         P01[s] = make_float2(FAR, FAR); P23[s] = make_float2(FAR, 1.f);
-        V01[s] = make_float2(0.f, 0.f); V23[s] = make_float2(0.f, 1.f);
-        PR[s] = 0.f;
+        V01[s] = make_float2(0.f, 0.f); RP[s] = make_float2(1.f, 0.f);
+        VZ[s] = 0.f;
     }
 
     ItemFetch nx;
@@ -611,27 +634,20 @@ k_force_list(SimParams sp, const int* __restrict__ cell_end, const int2* __restr
         // my warp's rows of the list pool, one block per pass: asked for now, needed after the staging
         const int row_p0 = item_row[(2 * it) * 8 + (tid >> 5)];
         const int row_p1 = npass > 1 ? item_row[(2 * it + 1) * 8 + (tid >> 5)] : row_p0;
-        // ---- stage the tile: candidate e in slot cand_to_slot(e); two candidates per thread and round,
-        //      all six loads in flight before the first store (psi comes ready-made from the density walk: D.z)
-        for (int e0 = tid; e0 < G.total; e0 += 2 * NB_THREADS) {
-            const int e1 = e0 + NB_THREADS;
-            const bool two = e1 < G.total;
-            const int g0 = tile_to_global(R, e0), g1 = two ? tile_to_global(R, e1) : g0;
-            const float4 p0 = Pin[g0], v0 = Vin[g0], d0 = D[g0];
-            const float4 p1 = Pin[g1], v1 = Vin[g1], d1 = D[g1];
-            {
-                const int sl = cand_to_slot(e0);
-                P01[sl] = make_float2(p0.x, p0.y); P23[sl] = make_float2(p0.z, d0.z);
-                V01[sl] = make_float2(v0.x, v0.y); V23[sl] = make_float2(v0.z, d0.x);
-                PR[sl] = d0.y;
-            }
-            if (two) {
-                const int sl = cand_to_slot(e1);
-                P01[sl] = make_float2(p1.x, p1.y); P23[sl] = make_float2(p1.z, d1.z);
-                V01[sl] = make_float2(v1.x, v1.y); V23[sl] = make_float2(v1.z, d1.x);
-                PR[sl] = d1.y;
-            }
+        // ---- stage the tile: candidate e in slot cand_to_slot(e), six asynchronous copies each (psi comes ready-made
+        //      from the density walk: D.z)
+        for (int e = tid; e < G.total; e += NB_THREADS) {
+            const int g = tile_to_global(R, e);
+            const uint32_t s8 = tP01 + 8u * (uint32_t)cand_to_slot(e);
+            const float4 *pp = Pin + g, *vp = Vin + g, *dp = D + g;
+            cp_async8(s8, pp);                                                   // P01 = {x, y}
+            cp_async4(s8 + PLANE_B, &pp->z);                                     // P23 = {z, psi}
+            cp_async4(s8 + PLANE_B + 4u, &dp->z);
+            cp_async8(s8 + 2u * PLANE_B, vp);                                    // V01 = {vx, vy}
+            cp_async8(s8 + 3u * PLANE_B, dp);                                    // RP  = {rho_raw, p / rho_c^2}
+            cp_async4(tVZ + ((s8 - tP01) >> 1), &vp->z);                         // VZ  = vz
         }
+        cp_async_commit();
         // the lists were written by the density walk long ago (DRAM): pull the count row and the first list rows
         // of both passes into L2 while the tile is being staged
         if (row_p0 >= 0 && row_p1 >= 0) {
@@ -641,6 +657,7 @@ k_force_list(SimParams sp, const int* __restrict__ cell_end, const int2* __restr
                 prefetch_l2(Lg + (size_t)(row_p1 + r) * 32 + (tid & 31));
             }
         }
+        cp_async_wait_all();
         __syncthreads();
         for (int pass = 0; pass < npass; ++pass) {
             const int t_local = pass * PASS_T + (tid >> 3);
@@ -677,16 +694,16 @@ k_force_list(SimParams sp, const int* __restrict__ cell_end, const int2* __restr
                 if (k + 3 < nw) w2 = gl[(size_t)(k + 3) * 32];
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
-                    const uint32_t m1 = (cur >> (16 * h)) & 0xffu, m2 = (cur >> (16 * h + 8)) & 0xffu;
-                    const uint32_t a1 = sP + 64u * m1, a2 = sP + 64u * m2;
+                    const uint32_t m1 = h ? byte_of<2>(cur) : byte_of<0>(cur), m2 = h ? byte_of<3>(cur) : byte_of<1>(cur);
+                    const uint32_t a1 = sP + (m1 << 6), a2 = sP + (m2 << 6);
                     const float2 xy1 = lds_f32x2(a1), zp1 = lds_f32x2(a1 + PLANE_B);
-                    const float2 vxy1 = lds_f32x2(a1 + 2u * PLANE_B), vzr1 = lds_f32x2(a1 + 3u * PLANE_B);
-                    const float pr1 = lds_f32(sR + 32u * m1);
+                    const float2 vxy1 = lds_f32x2(a1 + 2u * PLANE_B), rp1 = lds_f32x2(a1 + 3u * PLANE_B);
+                    const float vz1 = lds_f32(sVZ + (m1 << 5));
                     const float2 xy2 = lds_f32x2(a2), zp2 = lds_f32x2(a2 + PLANE_B);
-                    const float2 vxy2 = lds_f32x2(a2 + 2u * PLANE_B), vzr2 = lds_f32x2(a2 + 3u * PLANE_B);
-                    const float pr2 = lds_f32(sR + 32u * m2);
-                    pair_force2<HAS_BOUNDARY, SPLIT>(sp, C, pi, vi, rho_i, pr_i, xy1, zp1, vxy1, vzr1, pr1,
-                                                     xy2, zp2, vxy2, vzr2, pr2, A);
+                    const float2 vxy2 = lds_f32x2(a2 + 2u * PLANE_B), rp2 = lds_f32x2(a2 + 3u * PLANE_B);
+                    const float vz2 = lds_f32(sVZ + (m2 << 5));
+                    pair_force2<HAS_BOUNDARY, SPLIT>(sp, C, pi, vi, rho_i, pr_i, xy1, zp1, vxy1, make_float2(vz1, rp1.x), rp1.y,
+                                                     xy2, zp2, vxy2, make_float2(vz2, rp2.x), rp2.y, A);
                 }
             }
             float a6[6] = {A.anx.x + A.anx.y, A.any.x + A.any.y, A.anz.x + A.anz.y,
