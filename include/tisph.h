@@ -254,6 +254,14 @@ int tisph_shard_config(tisph_ctx *ctx, int32_t plane_lo, int32_t plane_hi, int32
 /* Particles per x-plane (gx values) as of the last completed step, ghosts included: a rank reads
  * its own planes [plane_lo, plane_hi) from it to feed the global histogram that places the faces. */
 int tisph_plane_counts(tisph_ctx *ctx, int32_t *counts);
+/* The same at (x-plane, y-row) granularity: a rank owns the cell rows r = cx * gy + cy in [row_lo, row_hi) -- still
+ * one contiguous key range of the sorted arrays -- so that equal-count slabs differ by one cell row (a few
+ * hundred particles) instead of one plane.  The halo of a neighbour is every particle with one of the
+ * neighbour's cells within ghost_planes cell layers in x and y.  tisph_shard_config(lo, hi, ...) is
+ * tisph_shard_config_rows(lo * gy, hi * gy, ...).  tisph_row_counts: gx * gy values, like tisph_plane_counts. */
+int tisph_shard_config_rows(tisph_ctx *ctx, int32_t row_lo, int32_t row_hi, int32_t ghost_planes,
+                            int32_t left_row_lo, int32_t right_row_hi, int32_t message_capacity);
+int tisph_row_counts(tisph_ctx *ctx, int32_t *counts);
 /* Fill the two send buffers from the owned particles: every particle within ghost_planes of a
  * slab face, or beyond it (a migrant), goes to that neighbour.  Synchronous; returns counts. */
 int tisph_shard_pack(tisph_ctx *ctx, int32_t *n_left, int32_t *n_right);

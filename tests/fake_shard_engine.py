@@ -33,8 +33,16 @@ class FakeShardEngine:
 
     # ---- Engine surface used by ShardedSim
     def shard_config(self, plane_lo, plane_hi, ghost, left_lo, right_hi, cap):
-        self.plane_lo, self.plane_hi, self.ghost = plane_lo, plane_hi, ghost
-        self.has_left, self.has_right, self.cap = left_lo >= 0, right_hi >= 0, cap
+        gy = int(self.config.grid_num[1])
+        self.shard_config_rows(plane_lo * gy, plane_hi * gy, ghost, left_lo * gy if left_lo >= 0 else -1,
+                               right_hi * gy if right_hi >= 0 else -1, cap)
+
+    def shard_config_rows(self, row_lo, row_hi, ghost, left_row_lo, right_row_hi, cap):
+        self.row_lo, self.row_hi, self.ghost = row_lo, row_hi, ghost
+        self.has_left, self.has_right, self.cap = left_row_lo >= 0, right_row_hi >= 0, cap
+
+    def _cells(self):
+        return (self.x[:, 0] / self.h).astype(np.int32), (self.x[:, 1] / self.h).astype(np.int32)
 
     def set_param(self, param, value):
         if param == K.P_ID_BASE:
@@ -63,9 +71,13 @@ class FakeShardEngine:
         return torch.from_numpy(rec)
 
     def shard_pack(self):
-        cx = (self.x[:, 0] / self.h).astype(np.int32)
-        left = (cx < self.plane_lo + self.ghost) if self.has_left else np.zeros(len(cx), bool)
-        right = (cx >= self.plane_hi - self.ghost) if self.has_right else np.zeros(len(cx), bool)
+        # the neighbour needs every particle that has one of ITS cell rows within `ghost` layers in x and y
+        cx, cy = self._cells()
+        gx, gy, g = int(self.config.grid_num[0]), int(self.config.grid_num[1]), self.ghost
+        lowest = np.maximum(cx - g, 0) * gy + np.maximum(cy - g, 0)
+        highest = np.minimum(cx + g, gx - 1) * gy + np.minimum(cy + g, gy - 1)
+        left = (lowest < self.row_lo) if self.has_left else np.zeros(len(cx), bool)
+        right = (highest >= self.row_hi) if self.has_right else np.zeros(len(cx), bool)
         self.msg[0], self.msg[1] = self._records(left), self._records(right)
         assert len(self.msg[0]) <= self.cap and len(self.msg[1]) <= self.cap
         return len(self.msg[0]), len(self.msg[1])
@@ -95,9 +107,9 @@ class FakeShardEngine:
                     pressure=self.pressure[order], volume=self.volume[order], mass=self.mass[order])
         o.orig = self.orig[order].copy()
         o.step()
-        # owned = x-plane at sort time in [plane_lo, plane_hi); everything else was a ghost
-        own = (o.keys // (int(self.config.grid_num[1]) * int(self.config.grid_num[2])))
-        own = (own >= self.plane_lo) & (own < self.plane_hi)
+        # owned = cell row at sort time in [row_lo, row_hi); everything else was a ghost
+        own = o.keys // int(self.config.grid_num[2])                     # cell row cx * gy + cy
+        own = (own >= self.row_lo) & (own < self.row_hi)
         self.x, self.v = o.x[own], o.v[own]
         self.mass, self.volume = o.mass[own], o.volume[own]
         self.density, self.pressure = o.density[own], o.pressure[own]
@@ -114,6 +126,11 @@ class FakeShardEngine:
     def plane_counts(self):
         cx = (self.x[:, 0] / self.h).astype(np.int32)
         return np.bincount(cx, minlength=int(self.config.grid_num[0])).astype(np.int32)
+
+    def row_counts(self):
+        cx, cy = self._cells()
+        gx, gy = int(self.config.grid_num[0]), int(self.config.grid_num[1])
+        return np.bincount(cx * gy + cy, minlength=gx * gy).astype(np.int32)
 
     def download(self, field, out=None):
         return {K.F_X: self.x, K.F_V: self.v, K.F_MATERIAL: self.material, K.F_ORIG_ID: self.orig,

@@ -55,6 +55,35 @@ def test_scene_parts_cover_the_scene_exactly_once():
     assert seen.all()
 
 
+def test_row_granular_slabs_cover_the_scene_exactly_once_and_balance_to_a_row():
+    """slabs cut at (x-plane, y-row) granularity: contiguous id chunks, every particle once, loads equal to
+    within one cell row of particles"""
+    scene = sc.bench_scene("C2")
+    parts = SceneParts(scene)
+    gy = int(parts.grid_num[1])
+    rows = parts.row_counts()
+    assert rows.sum() == parts.total and np.array_equal(rows.reshape(-1, gy).sum(axis=1), parts.plane_counts())
+    full = sc.cube_positions([0.3, 0.1, 0.7], [0.7, 0.9, 0.3], 0.01, 3)
+    assert np.array_equal(np.bincount(parts.row_of(full), minlength=len(rows)), rows)
+    for world in (2, 3, 5):
+        edges = plan_slabs(rows, world, min_planes=3 * gy)
+        seen = np.zeros(parts.total, bool)
+        loads = []
+        for a, b in zip(edges, edges[1:]):
+            n = 0
+            for id0, pos, vel, dens, mat in parts.slab_particles_rows(a, b):
+                assert np.array_equal(pos, full[id0:id0 + len(pos)])
+                assert not seen[id0:id0 + len(pos)].any()
+                seen[id0:id0 + len(pos)] = True
+                r = parts.row_of(pos)
+                assert np.all((r >= a) & (r < b))
+                n += len(pos)
+            loads.append(n)
+        assert seen.all()
+        assert max(loads) - min(loads) <= 2 * rows.max()          # whole planes: up to a plane (7 440 here) apart
+        assert any(e % gy for e in edges[1:-1])                   # at least one face inside a plane
+
+
 def _free_port():
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
@@ -126,7 +155,7 @@ def test_rebalancing_moves_the_faces_and_loses_nobody():
         mp.spawn(_worker, args=(world, _free_port(), "reference", steps, tmp, bad_edges, 2), nprocs=world, join=True)
         out = np.load(os.path.join(tmp, "out.npz"))
         owned = [np.load(os.path.join(tmp, f"owned{r}.npy")) for r in range(world)]
-    assert list(out["edges"]) != bad_edges
+    assert list(out["edges"]) != [25 * e for e in bad_edges]           # (faces are kept in cell rows: 25 per plane here)
     ora = Gen2Oracle(_scene())
     n = ora.n
     assert all(sum(o[s] for o in owned) == n for s in range(steps + 1))

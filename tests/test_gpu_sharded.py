@@ -98,7 +98,8 @@ def test_local_cluster_with_boundary_particles(vmode, dmode):
     scene = copy.deepcopy(_scene())
     g = np.arange(0.28, 0.46, 0.02)
     slab = np.stack(np.meshgrid(g, [0.26, 0.28], np.arange(0.28, 0.40, 0.02), indexing="ij"), -1).reshape(-1, 3).astype(np.float32)
-    slab = slab[np.argsort(x_plane(slab[:, 0], 0.04), kind="stable")]          # ids follow x-planes (SceneParts)
+    # ids follow the cell rows cx * gy + cy (SceneParts); gy = 25 cells of 0.04 in a unit domain
+    slab = slab[np.argsort(x_plane(slab[:, 0], 0.04) * 25 + x_plane(slab[:, 1], 0.04), kind="stable")]
     scene["rigidBodies"] = [{"geometryFile": "(points)", "scale": [1, 1, 1], "translation": [0, 0, 0], "rotationAngle": 0,
                              "rotationAxis": [0, 1, 0], "color": [255, 255, 255], "velocity": [0.0, 0.0, 0.0], "density": 1000.0}]
     cl = LocalCluster(scene, 3, density_mode=dmode, volume_mode=vmode, rigid_points=[slab])
@@ -120,10 +121,12 @@ def test_local_cluster_with_boundary_particles(vmode, dmode):
 
 
 def test_local_cluster_one_million_particles():
-    """C3 (1 M particles) cut into 4 slabs: one step bit-identical in order, 1e-5 in fields"""
+    """C3 (1 M particles) cut into 4 slabs at cell-row granularity: one step bit-identical in order, 1e-5 in fields"""
     from ti_sph_b200 import scene as sc
     scene = sc.bench_scene("C3")
     cl = LocalCluster(scene, 4)
+    owned = [s.engine.particle_num for s in cl.sims]
+    assert max(owned) - min(owned) <= 2 * 16 * 100 and any(s.row_lo % s.gy for s in cl.sims[1:])    # faces inside a plane
     ora = Gen2Oracle(scene)
     t = ora.step(trace=True); cl.step(1)
     d = cl.dump()
@@ -135,8 +138,8 @@ def test_local_cluster_one_million_particles():
 
 
 def test_local_cluster_rebalancing():
-    """lopsided slabs, re-balanced after two steps (tisph_plane_counts + re-issued
-    tisph_shard_config): faces move, nobody is lost, results still follow the oracle"""
+    """lopsided slabs, re-balanced after two steps (tisph_row_counts + re-issued
+    tisph_shard_config_rows): faces move, nobody is lost, results still follow the oracle"""
     bad_edges = [0, 8, 11, 25]
     cl = LocalCluster(_scene(), 3, edges=bad_edges)
     ora = Gen2Oracle(_scene())
@@ -145,8 +148,8 @@ def test_local_cluster_rebalancing():
     dens0, mat0 = ora.density.copy(), ora.material.copy()
     for s in range(5):
         if s == 2:
-            new = cl.rebalance()
-            assert new != bad_edges and all(b - a >= 3 for a, b in zip(new, new[1:]))
+            new = cl.rebalance()               # faces in cell rows (25 per plane here), not necessarily whole planes
+            assert new != [25 * e for e in bad_edges] and all(b - a >= 3 * 25 for a, b in zip(new, new[1:]))
         t = ora.step(trace=True); cl.step(1)
         d = cl.dump()
         ids = d["orig_id"]

@@ -83,6 +83,8 @@ SYMBOLS = {
     "tisph_shard_buffer": (C.c_int, [_vp, _i32, C.POINTER(_vp), _ip]),
     "tisph_shard_append": (C.c_int, [_vp, _i32, _i32]),
     "tisph_plane_counts": (C.c_int, [_vp, _vp]),
+    "tisph_shard_config_rows": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _i32]),
+    "tisph_row_counts": (C.c_int, [_vp, _vp]),
     "tisph_shard_ipc_export": (C.c_int, [_vp, _vp, C.c_size_t]),
     "tisph_shard_ipc_connect": (C.c_int, [_vp, _i32, _vp, C.c_size_t]),
     "tisph_shard_ipc_disconnect": (C.c_int, [_vp]),

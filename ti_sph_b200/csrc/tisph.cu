@@ -98,7 +98,7 @@ struct tisph_ctx {
     // slab sharding (tisph_shard.cuh)
     int *rank_key = nullptr;
     bool sharded = false;
-    int plane_lo = 0, plane_hi = 0, ghost = 1, left_lo = -1, right_hi = -1;   // neighbours' far edges, -1 = no neighbour
+    int row_lo = 0, row_hi = 0, ghost = 1, left_row_lo = -1, right_row_hi = -1;   // cell rows cx * gy + cy; neighbours' far edges, -1 = no neighbour
     int in_off = 0;                    // first record of the input slice inside P/V/Q[cur]
     bool appended = false;             // between tisph_shard_append and the step
     int o_lo = 0, o_hi = 0;            // owned slice of the sorted arrays (host copy)
@@ -1088,22 +1088,36 @@ int tisph_stage_times(tisph_ctx* c, int32_t enable, float* ms_update, float* ms_
 int tisph_shard_config(tisph_ctx* c, int32_t plane_lo, int32_t plane_hi, int32_t ghost_planes,
                        int32_t left_lo, int32_t right_hi, int32_t message_capacity) {
     CHECK_CTX(c);
+    const int gy = c->sp.gy;
+    if (plane_lo < 0 || plane_hi > c->sp.gx || plane_lo >= plane_hi)
+        return fail(TISPH_ERR_INVALID, "bad slab [%d,%d) of %d planes", plane_lo, plane_hi, c->sp.gx);
+    return tisph_shard_config_rows(c, plane_lo * gy, plane_hi * gy, ghost_planes, left_lo < 0 ? -1 : left_lo * gy,
+                                   right_hi < 0 ? -1 : right_hi * gy, message_capacity);
+}
+
+int tisph_shard_config_rows(tisph_ctx* c, int32_t row_lo, int32_t row_hi, int32_t ghost_planes,
+                            int32_t left_row_lo, int32_t right_row_hi, int32_t message_capacity) {
+    CHECK_CTX(c);
+    if (c->cfg.generation != 2) return fail(TISPH_ERR_INVALID, "slabs exist in the 3D path only");
     if (c->phase != 0 || c->appended) return fail(TISPH_ERR_INVALID, "slabs can only be (re)configured between steps");
     if (!c->sharded && c->have_sorted) return fail(TISPH_ERR_INVALID, "turn sharding on before the first step");
     const bool reconfig = c->sharded;           // moving the slab faces: the particles that fall outside the new
-                                                // planes leave with the next pack, like any other migrant
-    if (plane_lo < 0 || plane_hi > c->sp.gx || plane_lo >= plane_hi || ghost_planes < 1 || ghost_planes > 2 ||
-        message_capacity <= 0 || left_lo >= plane_lo || (right_hi >= 0 && right_hi <= plane_hi))
-        return fail(TISPH_ERR_INVALID, "bad slab [%d,%d) / ghost %d / capacity %d", plane_lo, plane_hi,
+                                                // rows leave with the next pack, like any other migrant
+    const int rows = c->sp.gx * c->sp.gy;
+    if (row_lo < 0 || row_hi > rows || row_lo >= row_hi || ghost_planes < 1 || ghost_planes > 2 ||
+        message_capacity <= 0 || left_row_lo >= row_lo || (right_row_hi >= 0 && right_row_hi <= row_hi))
+        return fail(TISPH_ERR_INVALID, "bad slab rows [%d,%d) / ghost %d / capacity %d", row_lo, row_hi,
                     ghost_planes, message_capacity);
     c->sharded = true;
-    c->plane_lo = plane_lo; c->plane_hi = plane_hi; c->ghost = ghost_planes;
-    c->left_lo = left_lo < 0 ? -1 : left_lo; c->right_hi = right_hi < 0 ? -1 : right_hi;
-    const int plane = c->sp.gy * c->sp.gz;
-    c->sp.own_key_lo = plane_lo * plane;
-    c->sp.own_key_hi = plane_hi * plane;
-    c->sp.walk_key_lo = (plane_lo - 1 > 0 ? plane_lo - 1 : 0) * plane;
-    c->sp.walk_key_hi = (plane_hi + 1 < c->sp.gx ? plane_hi + 1 : c->sp.gx) * plane;
+    c->row_lo = row_lo; c->row_hi = row_hi; c->ghost = ghost_planes;
+    c->left_row_lo = left_row_lo < 0 ? -1 : left_row_lo; c->right_row_hi = right_row_hi < 0 ? -1 : right_row_hi;
+    const int gz = c->sp.gz, gy = c->sp.gy;
+    c->sp.own_key_lo = row_lo * gz;
+    c->sp.own_key_hi = row_hi * gz;
+    // the density walk covers one cell layer around the owned rows: every cell (cx +- 1, cy +- 1) lies within
+    // gy + 1 rows of its centre
+    c->sp.walk_key_lo = (row_lo - gy - 1 > 0 ? row_lo - gy - 1 : 0) * gz;
+    c->sp.walk_key_hi = (row_hi + gy + 1 < rows ? row_hi + gy + 1 : rows) * gz;
     if (message_capacity != c->msg_cap) {
         if (c->peer[0][0] || c->peer[1][0])
             return fail(TISPH_ERR_INVALID, "the message capacity cannot change once peers have mapped the buffers");
@@ -1164,6 +1178,21 @@ int tisph_plane_counts(tisph_ctx* c, int32_t* counts) {
     return TISPH_OK;
 }
 
+int tisph_row_counts(tisph_ctx* c, int32_t* counts) {
+    CHECK_CTX(c);
+    if (!counts) return fail(TISPH_ERR_INVALID, "null argument");
+    if (c->cfg.generation != 2) return fail(TISPH_ERR_INVALID, "cell rows exist in the 3D path only");
+    if (!c->have_sorted || c->phase != 0) return fail(TISPH_ERR_INVALID, "row counts are those of the last completed step");
+    // particles per cell row (cx, cy) at the last sort = differences of the inclusive scan at the row ends
+    const int rows = c->sp.gx * c->sp.gy, gz = c->sp.gz;
+    std::vector<int> ends((size_t)rows);
+    CU(cudaMemcpy2DAsync(ends.data(), sizeof(int), c->cell_end + (gz - 1), (size_t)gz * sizeof(int), sizeof(int),
+                         (size_t)rows, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    for (int r = 0; r < rows; ++r) counts[r] = ends[r] - (r ? ends[r - 1] : 0);
+    return TISPH_OK;
+}
+
 int tisph_shard_pack(tisph_ctx* c, int32_t* n_left, int32_t* n_right) {
     CHECK_CTX(c);
     if (!c->sharded) return fail(TISPH_ERR_INVALID, "tisph_shard_config has not been called");
@@ -1177,7 +1206,7 @@ int tisph_shard_pack(tisph_ctx* c, int32_t* n_left, int32_t* n_right) {
     c->pack_seq++;
     if (n_upper > 0) {
         k_shard_pack<<<nblocks(n_upper, 256), 256, 0, st>>>(
-            c->sp, n_upper, c->range_dev, c->plane_lo, c->plane_hi, c->ghost, c->left_lo, c->right_hi,
+            c->sp, n_upper, c->range_dev, c->row_lo, c->row_hi, c->ghost, c->left_row_lo, c->right_row_hi,
             c->msg_cap, c->P[c->cur], c->V[c->cur], c->Q[c->cur],
             c->peer[0][par] ? c->peer[0][par] : c->msg[0], c->peer[1][par] ? c->peer[1][par] : c->msg[1], c->shard_ctr);
         c->launches += 1;

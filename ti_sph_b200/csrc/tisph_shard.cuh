@@ -1,13 +1,13 @@
 // tisph_shard.cuh -- spatial-slab sharding of the step across GPUs (one process per GPU).
 //
 // The reference is single-device (no distributed code).  The cell key is x-major
-// (key = cx*ny*nz + cy*nz + cz, partice_systemv4.py:98-100), so a slab of x-planes [plane_lo,
-// plane_hi) is one contiguous range of the sorted arrays, and so is every ghost plane.  A rank
+// (key = cx*ny*nz + cy*nz + cz, partice_systemv4.py:98-100), so a slab of cell rows (cx, cy) in
+// [row_lo, row_hi), row = cx*ny + cy, is one contiguous range of the sorted arrays.  A rank
 //   1. packs, from the particles it advanced in the previous step, those that now lie within
-//      `ghost` planes of a slab face or beyond it (migrants) into one message per neighbour,
+//      `ghost` cell layers of a neighbour's rows or inside them (migrants) into one message per neighbour,
 //   2. appends what the neighbours sent to its own slice and sorts everything together,
-//   3. runs the density walk on planes [plane_lo-1, plane_hi] and the force walk on its own planes.
-// Ownership is decided by position alone after the sort (cx in [plane_lo, plane_hi)); a migrant
+//   3. runs the density walk on its rows plus one layer around them and the force walk on its own rows.
+// Ownership is decided by position alone after the sort (row in [row_lo, row_hi)); a migrant
 // stays in the sender's arrays for one more step, where it is a ghost.
 #pragma once
 #include "tisph_device.cuh"
@@ -33,27 +33,34 @@ __global__ void k_owned_range(const int* __restrict__ cell_end, int ncell, int o
 
 // Pack the messages.  `range` = {first, end} of the owned slice inside P/V/Q (device memory, so
 // that no host round trip is needed between the step and the pack).
+// Slabs are cut at (x-plane, y-row) granularity: a rank owns the cell ROWS r = cx * gy + cy in [row_lo, row_hi) --
+// still one contiguous key range.  The left neighbour owns rows below row_lo: it needs every particle of mine that
+// has one of ITS cells within `ghost` cell layers (in x and y), i.e. whose lowest such row
+// max(cx - ghost, 0) * gy + max(cy - ghost, 0) is below row_lo; migrants (own row below row_lo) are among them.
 __global__ void __launch_bounds__(256)
-k_shard_pack(SimParams sp, int n_upper, const int* __restrict__ range, int plane_lo, int plane_hi,
-             int ghost, int left_lo, int right_hi, int cap_records,
+k_shard_pack(SimParams sp, int n_upper, const int* __restrict__ range, int row_lo, int row_hi,
+             int ghost, int left_row_lo, int right_row_hi, int cap_records,
              const float4* __restrict__ P, const float4* __restrict__ V, const float4* __restrict__ Q,
              float4* __restrict__ send_left, float4* __restrict__ send_right,
              ShardCounters* __restrict__ ctr) {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     int first = range[0], end = range[1];
     int i = first + t;
-    const bool has_left = left_lo >= 0, has_right = right_hi >= 0;
+    const bool has_left = left_row_lo >= 0, has_right = right_row_hi >= 0;
     bool valid = t < n_upper && i < end;
     bool to_left = false, to_right = false;
     float4 p, v, q;
     if (valid) {
         p = P[i];
-        int cx = cell_coord(p.x, sp.h);
-        to_left = has_left && cx < plane_lo + ghost;
-        to_right = has_right && cx >= plane_hi - ghost;
-        // a migrant may land anywhere inside the neighbour's slab [left_lo, plane_lo) / [plane_hi, right_hi);
+        const int cx = cell_coord(p.x, sp.h), cy = cell_coord(p.y, sp.h);
+        const int row = cx * sp.gy + cy;
+        const int lowest = max(cx - ghost, 0) * sp.gy + max(cy - ghost, 0);
+        const int highest = min(cx + ghost, sp.gx - 1) * sp.gy + min(cy + ghost, sp.gy - 1);
+        to_left = has_left && lowest < row_lo;
+        to_right = has_right && highest >= row_hi;
+        // a migrant may land anywhere inside the neighbour's slab [left_row_lo, row_lo) / [row_hi, right_row_hi);
         // beyond it the neighbour would not own it either
-        if ((has_left && cx < left_lo) || (has_right && cx >= right_hi)) atomicAdd(&ctr->lost, 1);
+        if ((has_left && row < left_row_lo) || (has_right && row >= right_row_hi)) atomicAdd(&ctr->lost, 1);
         if (to_left || to_right) { v = V[i]; q = Q[i]; }
     }
     // warp-aggregated slot reservation

@@ -183,6 +183,18 @@ class Engine:
                                            int(left_lo), int(right_hi), int(message_capacity)))
         self._msg_cap = int(message_capacity)
 
+    def shard_config_rows(self, row_lo, row_hi, ghost_planes, left_row_lo, right_row_hi, message_capacity):
+        """slab of the cell rows cx * gy + cy in [row_lo, row_hi); far edges of the neighbours, -1 = no neighbour"""
+        check(self._lib.tisph_shard_config_rows(self._ctx, int(row_lo), int(row_hi), int(ghost_planes),
+                                                int(left_row_lo), int(right_row_hi), int(message_capacity)))
+        self._msg_cap = int(message_capacity)
+
+    def row_counts(self):
+        """particles per cell row (cx, cy) at the last sort (ghosts included), gx * gy values"""
+        out = np.zeros(int(self.config.grid_num[0]) * int(self.config.grid_num[1]), np.int32)
+        check(self._lib.tisph_row_counts(self._ctx, _ptr(out)))
+        return out
+
     def plane_counts(self):
         """particles per x-plane at the last sort (ghosts included)"""
         out = np.zeros(int(self.config.grid_num[0]), np.int32)

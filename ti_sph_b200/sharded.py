@@ -1,22 +1,24 @@
 """Slab-sharded WCSPH step: one process (and one Engine) per GPU, x-slabs, halo exchange + migration.
 
 The reference is single-device; this is the multi-GPU row of SURVEY.md 8(e).
-The cell key is x-major (partice_systemv4.py:98-100), so a rank that owns the x-planes
-[plane_lo, plane_hi) of the grid owns one contiguous range of the sorted particle arrays, and its
-ghost planes are contiguous too: a halo message is a plain run of 48-byte records, packed by one
-kernel (csrc/tisph_shard.cuh) and sent with NCCL send/recv over NVLink -- there is no all-reduce
-or any other collective on the data path.  Per step and rank:
+The cell key is x-major (partice_systemv4.py:98-100), so a rank that owns the cell ROWS
+row = cx * gy + cy in [row_lo, row_hi) -- whole x-planes plus a partial plane at either end -- owns one
+contiguous range of the sorted particle arrays.  A halo message is a plain run of 48-byte records, packed
+by one kernel (csrc/tisph_shard.cuh) and written peer-to-peer over NVLink (or sent with NCCL send/recv)
+-- there is no all-reduce or any other collective on the data path.  Per step and rank:
 
-    pack  (owned particles within `ghost` planes of a face, or beyond it = migrants)
+    pack  (owned particles with a cell of the neighbour within `ghost` cell layers, or inside the
+           neighbour's rows = migrants)
     -> exchange counts with both neighbours -> exchange records
-    -> append -> bin/scan/sort everything -> density on [lo-1, hi] -> forces/advect on [lo, hi)
+    -> append -> bin/scan/sort everything -> density on the owned rows + one layer -> forces/advect on the owned rows
 
 `ghost` is 1 when a particle's density needs no neighbour data (density_mode "reference" with
 volume_mode "reference": rho = mass W(0), wcsphv2.py:32-34), else 2 -- the densities of the first
 ghost plane are then recomputed locally instead of being exchanged a second time.
 
-Slab edges are chosen once from the per-x-plane particle histogram so that every rank starts
-with the same number of particles (`plan_slabs`).  Intra-cell order is by original particle id
+Slab edges are chosen once from the per-row particle histogram so that every rank starts with the
+same number of particles to within one cell row (`plan_slabs`; round 1 cut at whole planes: 4 % imbalance
+at 8 ranks of the 16 M-particle scene).  Intra-cell order is by original particle id
 (the single-GPU engine orders by array position like the serial reference; array positions are
 rank-local here).  Concatenating the ranks' owned particles in rank order gives the global
 cell-sorted order that ParticleSystemV4.dump() of a single engine returns.
@@ -42,7 +44,8 @@ def x_plane(x, h):
 def plan_slabs(plane_counts, world, min_planes=3):
     """Edges e[0]=0 < e[1] < ... < e[world]=len(plane_counts): slab k owns planes [e[k], e[k+1]).
     Cuts are put where the cumulative particle count crosses k/world of the total; every slab is
-    at least `min_planes` thick (the ghost-layer argument of the module docstring needs 3)."""
+    at least `min_planes` thick (the ghost-layer argument of the module docstring needs 3).
+    Works the same on a per-ROW histogram (units = cell rows, min_planes = 3 * gy)."""
     counts = np.asarray(plane_counts, np.int64)
     gx = len(counts)
     if world * min_planes > gx:
@@ -81,7 +84,7 @@ class SceneParts:
         nid = 0
         for body, pts in zip(scene["rigidBodies"], rigid_points):
             pts = np.asarray(pts, np.float32)
-            order = np.argsort(x_plane(pts[:, 0], self.h), kind="stable")   # ids follow x-planes
+            order = np.argsort(self.row_of(pts), kind="stable")             # ids follow the cell rows
             self.parts.append(("rigid", nid, (pts[order], body)))
             nid += len(pts)
         for blk in scene["fluidBlocks"]:
@@ -94,6 +97,23 @@ class SceneParts:
             self.parts.append(("fluid", nid, (axes, blk)))
             nid += n
         self.total = nid
+
+    def row_of(self, pts):
+        """cell row cx * gy + cy of positions (n, 3)"""
+        return x_plane(pts[:, 0], self.h).astype(np.int64) * int(self.grid_num[1]) + x_plane(pts[:, 1], self.h)
+
+    def row_counts(self):
+        """particles per cell row (cx, cy): gx * gy values"""
+        gx, gy = int(self.grid_num[0]), int(self.grid_num[1])
+        counts = np.zeros(gx * gy, np.int64)
+        for kind, _, data in self.parts:
+            if kind == "rigid":
+                np.add.at(counts, self.row_of(data[0]), 1)
+            else:
+                axes, _ = data
+                px, py = x_plane(axes[0].astype(np.float32), self.h), x_plane(axes[1].astype(np.float32), self.h)
+                np.add.at(counts, (px[:, None].astype(np.int64) * gy + py[None, :]).ravel(), len(axes[2]))
+        return counts
 
     def plane_counts(self):
         counts = np.zeros(int(self.grid_num[0]), np.int64)
@@ -108,30 +128,55 @@ class SceneParts:
     def slab_particles(self, lo, hi):
         """[(id0, pos, vel, density, material)] of the particles whose x-plane is in [lo, hi);
         every chunk has contiguous original ids starting at id0."""
+        gy = int(self.grid_num[1])
+        return self.slab_particles_rows(lo * gy, hi * gy)
+
+    def slab_particles_rows(self, row_lo, row_hi):
+        """the same for the cell rows cx * gy + cy in [row_lo, row_hi).  A fluid block is a lattice with ids
+        x-major, then y, then z: the x-layers of a partial plane contribute one contiguous id range each."""
+        gy = int(self.grid_num[1])
         out = []
         for kind, id0, data in self.parts:
             if kind == "rigid":
                 pts, body = data
-                pl = x_plane(pts[:, 0], self.h)
-                a, b = int(np.searchsorted(pl, lo, "left")), int(np.searchsorted(pl, hi, "left"))
+                rows = self.row_of(pts)                                # non-decreasing (sorted in __init__)
+                a, b = int(np.searchsorted(rows, row_lo, "left")), int(np.searchsorted(rows, row_hi, "left"))
                 if b > a:
                     dens = body.get("density")
                     out.append((id0 + a, pts[a:b], np.tile(np.array(body["velocity"], np.float32), (b - a, 1)),
                                 np.full(b - a, dens if dens is not None else 1000.0, np.float32),
                                 np.zeros(b - a, np.int32)))
-            else:
-                axes, blk = data
-                pl = x_plane(axes[0].astype(np.float32), self.h)       # non-decreasing in x
-                a, b = int(np.searchsorted(pl, lo, "left")), int(np.searchsorted(pl, hi, "left"))
-                if b > a:
-                    per_layer = len(axes[1]) * len(axes[2])
-                    pos = np.array(np.meshgrid(axes[0][a:b], axes[1], axes[2], indexing="ij"), dtype=np.float32)
-                    pos = np.ascontiguousarray(pos.reshape(3, -1).T)
-                    dens = blk["density"]
-                    out.append((id0 + a * per_layer, pos,
-                                np.full(pos.shape, blk["velocity"], dtype=np.float32),
-                                np.full(len(pos), dens if dens is not None else 1000.0, np.float32),
-                                np.ones(len(pos), np.int32)))
+                continue
+            axes, blk = data
+            px = x_plane(axes[0].astype(np.float32), self.h).astype(np.int64)       # non-decreasing in x
+            py = x_plane(axes[1].astype(np.float32), self.h).astype(np.int64)       # ... and in y
+            ny, nz = len(axes[1]), len(axes[2])
+            dens = blk["density"]
+
+            def chunk(ia, ib, ja, jb):
+                """x-layers [ia, ib) x y-layers [ja, jb) x all z: contiguous ids when ja, jb cover all y or ib = ia + 1"""
+                pos = np.array(np.meshgrid(axes[0][ia:ib], axes[1][ja:jb], axes[2], indexing="ij"), dtype=np.float32)
+                pos = np.ascontiguousarray(pos.reshape(3, -1).T)
+                out.append((id0 + (ia * ny + ja) * nz, pos, np.full(pos.shape, blk["velocity"], dtype=np.float32),
+                            np.full(len(pos), dens if dens is not None else 1000.0, np.float32),
+                            np.ones(len(pos), np.int32)))
+
+            # x-layers whose whole plane is inside: one chunk; the others layer by layer with their y-range
+            full = (px * gy >= row_lo) & ((px + 1) * gy <= row_hi)
+            ia = 0
+            while ia < len(px):
+                if full[ia]:
+                    ib = ia
+                    while ib < len(px) and full[ib]:
+                        ib += 1
+                    chunk(ia, ib, 0, ny)
+                    ia = ib
+                    continue
+                rows = px[ia] * gy + py
+                ja, jb = int(np.searchsorted(rows, row_lo, "left")), int(np.searchsorted(rows, row_hi, "left"))
+                if jb > ja:
+                    chunk(ia, ia + 1, ja, jb)
+                ia += 1
         return out
 
     def color_of(self, ids):
@@ -246,7 +291,9 @@ class ShardedSim:
 
     def __init__(self, scene, rank, world, comm=None, density_mode="reference", volume_mode="reference",
                  device=0, rigid_points=(), engine_factory=None, capacity_factor=1.6, edges=None,
-                 message_capacity=None):
+                 message_capacity=None, row_edges=None):
+        """edges: slab faces in x-planes (whole planes); row_edges: in cell rows cx * gy + cy.  Default: equal
+        particle counts to within one cell row."""
         import torch
         self.torch = torch
         self.rank, self.world, self.comm = rank, world, comm
@@ -262,13 +309,20 @@ class ShardedSim:
         self.parts = SceneParts(scene, rigid_points)
         self.ghost = 1 if (density_mode == "reference" and volume_mode == "reference") else 2
         counts = self.parts.plane_counts()
-        self.edges = list(edges) if edges is not None else plan_slabs(counts, world)
-        self.plane_lo, self.plane_hi = self.edges[rank], self.edges[rank + 1]
+        self.gy = gy = int(self.parts.grid_num[1])
+        if row_edges is not None:
+            self.edges = [int(e) for e in row_edges]
+        elif edges is not None:
+            self.edges = [int(e) * gy for e in edges]
+        else:
+            self.edges = plan_slabs(self.parts.row_counts(), world, min_planes=3 * gy)
+        self.row_lo, self.row_hi = self.edges[rank], self.edges[rank + 1]
+        self.plane_lo, self.plane_hi = self.row_lo // gy, -(-self.row_hi // gy)     # the planes the slab touches
         self.has_left, self.has_right = rank > 0, rank < world - 1
-        chunks = self.parts.slab_particles(self.plane_lo, self.plane_hi)
+        chunks = self.parts.slab_particles_rows(self.row_lo, self.row_hi)
         n_own = sum(len(c[1]) for c in chunks)
-        halo = int(counts[max(self.plane_lo - self.ghost, 0):self.plane_lo].sum() +
-                   counts[self.plane_hi:self.plane_hi + self.ghost].sum())
+        halo = int(counts[max(self.plane_lo - self.ghost, 0):self.plane_lo + 1].sum() +
+                   counts[max(self.plane_hi - 1, 0):self.plane_hi + self.ghost].sum())
         peak_plane = int(counts.max())
         if message_capacity is None:
             message_capacity = max(1024, 2 * (self.ghost + 1) * peak_plane)
@@ -280,9 +334,9 @@ class ShardedSim:
             from .engine import Engine
             engine_factory = Engine
         self.engine = eng = engine_factory(cfg)
-        eng.shard_config(self.plane_lo, self.plane_hi, self.ghost,
-                         self.edges[rank - 1] if self.has_left else -1,
-                         self.edges[rank + 2] if self.has_right else -1, message_capacity)
+        eng.shard_config_rows(self.row_lo, self.row_hi, self.ghost,
+                              self.edges[rank - 1] if self.has_left else -1,
+                              self.edges[rank + 2] if self.has_right else -1, message_capacity)
         if scene["rigidBodies"]:
             eng.set_param(K.P_HAS_BOUNDARY, 1)
         for id0, pos, vel, dens, mat in chunks:
@@ -401,38 +455,49 @@ class ShardedSim:
         return dt
 
     # -- re-balancing --------------------------------------------------------------------------
-    def owned_plane_counts(self):
-        """this rank's contribution to the global per-plane histogram (its own planes only)"""
-        counts = np.asarray(self.engine.plane_counts(), np.int64)
+    def owned_row_counts(self):
+        """this rank's contribution to the global per-row histogram (its own cell rows only)"""
+        counts = np.asarray(self.engine.row_counts(), np.int64)
         mine = np.zeros_like(counts)
-        mine[self.plane_lo:self.plane_hi] = counts[self.plane_lo:self.plane_hi]
+        mine[self.row_lo:self.row_hi] = counts[self.row_lo:self.row_hi]
         return mine
 
-    def apply_histogram(self, plane_counts):
-        """Move the slab faces to where `plane_counts` (global, identical on all ranks) says the
-        load is balanced.  A face moves at most to the old position of a neighbouring face, so
-        that every particle's new owner is the old owner or one of its neighbours and the next
-        pack can carry it there.  Must be called by all ranks between the same two steps."""
+    def owned_plane_counts(self):
+        """... summed over the rows of every x-plane"""
+        return self.owned_row_counts().reshape(-1, self.gy).sum(axis=1)
+
+    def apply_histogram(self, row_counts):
+        """Move the slab faces to where `row_counts` (global per-row histogram, identical on all ranks; a per-PLANE
+        histogram is accepted too and cuts at whole planes) says the load is balanced.  A face moves at most to
+        the old position of a neighbouring face, so that every particle's new owner is the old owner or one of
+        its neighbours and the next pack can carry it there.  Must be called by all ranks between the same two
+        steps."""
+        row_counts = np.asarray(row_counts, np.int64)
+        gy = self.gy
+        if len(row_counts) == int(self.parts.grid_num[0]):            # a per-plane histogram
+            want = [e * gy for e in plan_slabs(row_counts, self.world)]
+        else:
+            want = plan_slabs(row_counts, self.world, min_planes=3 * gy)
         old = self.edges
-        want = plan_slabs(plane_counts, self.world)
         new = [0]
         for k in range(1, self.world):
             e = min(max(want[k], old[k - 1]), old[k + 1])
-            e = max(e, new[-1] + 3)
-            e = min(e, old[-1] - 3 * (self.world - k))
+            e = max(e, new[-1] + 3 * gy)
+            e = min(e, old[-1] - 3 * gy * (self.world - k))
             new.append(int(e))
         new.append(old[-1])
         self.edges = new
         r = self.rank
-        self.plane_lo, self.plane_hi = new[r], new[r + 1]
-        self.engine.shard_config(self.plane_lo, self.plane_hi, self.ghost,
-                                 new[r - 1] if self.has_left else -1, new[r + 2] if self.has_right else -1,
-                                 self._message_capacity)
+        self.row_lo, self.row_hi = new[r], new[r + 1]
+        self.plane_lo, self.plane_hi = self.row_lo // gy, -(-self.row_hi // gy)
+        self.engine.shard_config_rows(self.row_lo, self.row_hi, self.ghost,
+                                      new[r - 1] if self.has_left else -1, new[r + 2] if self.has_right else -1,
+                                      self._message_capacity)
         return new
 
     def rebalance(self):
         """collective: gather the histogram, move the faces (see apply_histogram)"""
-        total = sum(self.comm.all_gather_objects(self.owned_plane_counts()))
+        total = sum(self.comm.all_gather_objects(self.owned_row_counts()))
         return self.apply_histogram(total)
 
     def close(self):
@@ -519,7 +584,7 @@ class LocalCluster:
                 s.compute()
 
     def rebalance(self):
-        total = sum(s.owned_plane_counts() for s in self.sims)
+        total = sum(s.owned_row_counts() for s in self.sims)
         return [s.apply_histogram(total) for s in self.sims][0]
 
     def dump(self):
