@@ -336,7 +336,8 @@ def run_gpu(args):
         stream = sim.stream                # engine kernels and NCCL exchanges are ordered on this stream
         torch.cuda.set_stream(stream)      # ... and so are the timing events
         n_total = sim.global_particle_num
-        log(f"[bench] rank {rank}: planes [{sim.plane_lo},{sim.plane_hi}) {sim.initial_owned} particles")
+        log(f"[bench] rank {rank}: cell rows [{sim.row_lo},{sim.row_hi}) of {sim.gy} per plane = planes "
+            f"[{sim.plane_lo},{sim.plane_hi}), {sim.initial_owned} particles")
         step = lambda k=1: sim.step(k)
 
     def barrier():
@@ -609,7 +610,9 @@ def main():
     ap.add_argument("--workload", default="C5", choices=["C2", "C3", "C4", "C5"])
     ap.add_argument("--mode", default="reference", choices=["reference", "summed"],
                     help="density mode: reference = bit-faithful to wcsphv2.py:32-34, summed = intent")
-    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--e2e-steps", type=int, default=20,
+                    help="steps of the end-to-end leg (the first upload and the last read-back are not overlapped by "
+                         "anything: over 5 steps they cost 3.7 ms per step at C5, over 20 less than 1)")
     ap.add_argument("--pre-steps", type=int, default=None,
                     help="steps from the lattice before the state is saved (default: 10; 2 in summed mode, where the "
                          "reference's fixed dt is beyond the CFL limit at r = 0.005 and the block disintegrates within ~10 steps)")
