@@ -234,26 +234,30 @@ class ShmCounts:
     live on this node (LOCAL_WORLD_SIZE == WORLD_SIZE), the NCCL path otherwise."""
 
     def __init__(self, comm, rank, world):
+        import mmap
         import os
-        from multiprocessing import shared_memory
+        import tempfile
         self.rank, self.world = rank, world
-        name = None
+        size = world * 64
+        # A plain file in /dev/shm mapped by every rank (multiprocessing.shared_memory would hand the segment to
+        # Python's resource tracker, which unlinks attached segments at exit and warns about "leaks").  Rank 0
+        # removes the name as soon as everybody has mapped it, so nothing is left behind even after a crash.
+        path = None
         if rank == 0:
-            self.shm = shared_memory.SharedMemory(create=True, size=world * 64)
-            self.shm.buf[:world * 64] = bytes(world * 64)
-            name = self.shm.name
-        name = comm.all_gather_objects(name)[0]
+            fd, path = tempfile.mkstemp(prefix="tisph_counts_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+            os.ftruncate(fd, size)
+        path = comm.all_gather_objects(path)[0]
         if rank != 0:
-            self.shm = shared_memory.SharedMemory(name=name)
-            # (Python < 3.13 also registers attached segments with the resource tracker, which prints a
-            # harmless "leaked shared_memory" warning at exit; only the creator unlinks.)
+            fd = os.open(path, os.O_RDWR)
+        self.mm = mmap.mmap(fd, size)
+        os.close(fd)
         # two slots per rank, used alternately: a rank can be at most one step ahead of a neighbour
         # (it needs the neighbour's counts of step k+1 before it can publish step k+2)
-        self.arr = np.ndarray((world, 2, 4), dtype=np.int64, buffer=self.shm.buf)
+        self.arr = np.ndarray((world, 2, 4), dtype=np.int64, buffer=self.mm)
         self.step = 0
-        comm.all_gather_objects(None)          # everybody attached before anybody publishes
-        import atexit
-        atexit.register(self.close)
+        comm.all_gather_objects(None)          # everybody attached before anybody publishes ...
+        if rank == 0:
+            os.unlink(path)                    # ... and before the name goes away
 
     def exchange(self, nl, nr, has_left, has_right):
         import time
@@ -277,10 +281,9 @@ class ShmCounts:
         return ml, mr
 
     def close(self):
+        self.arr = None
         try:
-            self.shm.close()
-            if self.rank == 0:
-                self.shm.unlink()
+            self.mm.close()
         except Exception:
             pass
 
