@@ -221,11 +221,30 @@ def run_reference_impl(args):
 
 
 # ----------------------------------------------------------------------------- GPU arm
-def also_measure(workload, mode, pre, chain, args, torch, stream, lists_only=False):
+def engine_at_spacing(workload, mode, factor, start, size):
+    """NOT a reference configuration: a block filled at `factor` x the reference's lattice spacing (the reference
+    puts particles one RADIUS apart, SURVEY Q7: h = 4 x spacing, 64 particles per cell; factor 2 is the conventional
+    one particle diameter: h = 2 x spacing, 8 per cell).  Same solver constants, grid and kernels."""
+    from ti_sph_b200 import scene as sc
+    from ti_sph_b200.engine import Engine
+    s = sc.bench_scene(workload)
+    cfg, blk = s["configuration"], s["fluidBlocks"][0]
+    x = sc.cube_positions(start, size, factor * cfg["particleRadius"], 3)
+    n = len(x)
+    eng = Engine(sc.gen2_config(cfg, n, density_mode={"reference": 0, "summed": 1}[mode]))
+    eng.add_particles(x, np.full(x.shape, blk["velocity"], np.float32), np.full(n, 1000.0, np.float32),
+                      np.zeros(n, np.float32), np.ones(n, np.int32), None)
+    return eng
+
+
+def also_measure(workload, mode, pre, chain, args, torch, stream, lists_only=False, spacing=None):
     """device-resident timing of a second workload / density mode with the rules of the main one (single GPU)"""
-    from core.partice_system.partice_systemv4 import ParticleSystemV4
-    ps = ParticleSystemV4(workload_scene(workload), density_mode=mode)
-    eng = ps.engine
+    if spacing is None:
+        from core.partice_system.partice_systemv4 import ParticleSystemV4
+        ps = ParticleSystemV4(workload_scene(workload), density_mode=mode)
+        eng = ps.engine
+    else:
+        eng = engine_at_spacing(workload, mode, *spacing)
     eng.set_stream(stream.cuda_stream)
     if lists_only:
         eng.set_param(_K().P_SKIP_DISCARDED_SUM, 1)
@@ -255,7 +274,13 @@ def also_measure(workload, mode, pre, chain, args, torch, stream, lists_only=Fal
     eng.close()
     extra = {"note": "opt-in TISPH_P_SKIP_DISCARDED_SUM: the density walk builds the neighbour lists only; the sum that "
                      "wcsphv2.py:32-34 overwrites is not evaluated. NOT the headline: the default computes it."} if lists_only else {}
-    return {**extra, "workload": f"{workload}: {n} particles", "density_mode": mode, "value": n / (ms * 1e-3), "unit": UNIT,
+    if spacing is not None:
+        extra = {"note": f"NOT a reference configuration (SURVEY 8(d), optional): block {spacing[1]} + {spacing[2]} filled at "
+                         f"{spacing[0]} x the reference's lattice spacing, i.e. one particle diameter apart (h = 2 x spacing: 216 "
+                         "candidates and ~30 neighbours per particle instead of 1728 and ~250). Shows how the HBM fraction moves "
+                         "with the neighbour count; the walk kernels are laid out for the reference's 64 particles per cell."}
+    label = f"{workload}: {n} particles" if spacing is None else f"{workload} grid, block at {spacing[0]} x the lattice spacing: {n} particles"
+    return {**extra, "workload": label, "density_mode": mode, "value": n / (ms * 1e-3), "unit": UNIT,
             "ms_per_step": ms, "stage_ms": {k: st[k] for k in ("update_ms", "density_ms", "force_ms")},
             "step_hbm_frac": BYTES_STEP[mode] * n / (ms * 1e-3) / 1e9 / measured_peaks()[0],
             "pair_interactions_per_s": None if lists_only else 2.0 * pairs / (ms * 1e-3), "fallback_force_items": fb,
@@ -587,9 +612,11 @@ def run_gpu(args):
         also = {}
         for key, (wl, mode, pre, chain, lo) in {"C3_1M": ("C3", args.mode, 50, 5, False),
                                                 "C5_16M_summed": ("C5", "summed", 2, 3, False),
-                                                "C5_16M_reference_lists_only": ("C5", "reference", 10, 5, True)}.items():
+                                                "C5_16M_reference_lists_only": ("C5", "reference", 10, 5, True),
+                                                "nonreference_spacing_2r_8M": ("C5", args.mode, 10, 5, False)}.items():
             try:
-                also[key] = also_measure(wl, mode, pre, chain, args, torch, stream, lists_only=lo)
+                also[key] = also_measure(wl, mode, pre, chain, args, torch, stream, lists_only=lo,
+                                         spacing=(2.0, [0.3, 0.1, 0.3], [4.0, 2.0, 1.0]) if key.startswith("nonreference") else None)
             except Exception as e:                  # never lose the main line over a side measurement
                 also[key] = {"error": str(e)[:200]}
         line["config"]["also"] = also
