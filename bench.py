@@ -613,7 +613,8 @@ def run_gpu(args):
         for key, (wl, mode, pre, chain, lo) in {"C3_1M": ("C3", args.mode, 50, 5, False),
                                                 "C5_16M_summed": ("C5", "summed", 2, 3, False),
                                                 "C5_16M_reference_lists_only": ("C5", "reference", 10, 5, True),
-                                                "nonreference_spacing_2r_8M": ("C5", args.mode, 10, 5, False)}.items():
+                                                **({"nonreference_spacing_2r_8M": ("C5", args.mode, 10, 5, False)}
+                                                   if args.also_spacing else {})}.items():
             try:
                 also[key] = also_measure(wl, mode, pre, chain, args, torch, stream, lists_only=lo,
                                          spacing=(2.0, [0.3, 0.1, 0.3], [4.0, 2.0, 1.0]) if key.startswith("nonreference") else None)
@@ -648,6 +649,8 @@ def main():
     ap.add_argument("--ref-particles", type=int, default=1000000, help="sample size of --impl reference")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-also", action="store_true", help="skip the side measurements of the C5 run (1 M particles; summed mode)")
+    ap.add_argument("--also-spacing", action="store_true",
+                    help="add the NON-reference side measurement at one-diameter lattice spacing (8 particles per cell) to config.also")
     ap.add_argument("--no-check", action="store_true", help="skip the sharded-vs-single-engine check of a multi-GPU run")
     args = ap.parse_args()
     if args.pre_steps is None:

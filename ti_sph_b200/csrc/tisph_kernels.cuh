@@ -250,6 +250,15 @@ __device__ __forceinline__ int tile_to_global(const CellRanges& R, int e) {
     return R.gb[k] + (e - R.off[k]);
 }
 
+// The same for a thread that visits its candidates in ASCENDING order (the staging loops): the range of a
+// candidate is found from the previous one's -- k only moves forward, one shared-memory compare per call
+// instead of eight.  k = 0 at the start of an item.  (R.off is non-decreasing, so "the last t with
+// off[t] <= e" is what tile_to_global counts; empty ranges are stepped over.)
+__device__ __forceinline__ int tile_to_global_fwd(const CellRanges& R, int e, int& k) {
+    while (k < 8 && e >= R.off[k + 1]) ++k;
+    return R.gb[k] + (e - R.off[k]);
+}
+
 // ---------------------------------------------------------------------------------------
 // Host<->device layout conversion (add_particles :171-204, dump/copy_to_numpy :279-307)
 // ---------------------------------------------------------------------------------------

@@ -254,36 +254,55 @@ k_density_list(SimParams sp, const int* __restrict__ cell_end, const int2* __res
         // centre of the target cell: origin of the half-precision coordinates
         const float ccx = ((float)(G.c / (sp.gz * sp.gy)) + 0.5f) * sp.h, ccy = ((float)((G.c / sp.gz) % sp.gy) + 0.5f) * sp.h,
                     ccz = ((float)(G.c % sp.gz) + 0.5f) * sp.h;
-        for (int p = tid; p < nrow2 * 8; p += NB_THREADS) {
-            const int k = p >> 3, jj = p & 7;
-            const int sa = 16 * k + jj, sb = sa + 8;                  // slots (rows 2k and 2k+1, lane class jj)
-            const int ea = slot_to_cand(sa), eb = slot_to_cand(sb);
-            float4 a = make_float4(FAR, FAR, FAR, 0.f), b = a;
-            float3 ua = make_float3(0.f, 0.f, 0.f), ub = ua;
-            bool va = false, vb = false;                                       // padding: never within the cutoff
-            int ma = MAT_FLUID, mb = MAT_FLUID;
-            if (ea < walk_total) {
-                const int g = tile_to_global(R, ea);
-                a = P[g]; va = true;
-                ua = make_float3((a.x - ccx) * sp.inv_h, (a.y - ccy) * sp.inv_h, (a.z - ccz) * sp.inv_h);
-                if (AKINCI) ma = __float_as_int(Q[g].z);
+        // Two records (p, p + 256) per iteration: the four candidates' global rows first -- each of the two candidate
+        // sequences of a thread ascends, so their ranges are found incrementally -- then all four loads, then the
+        // conversions: the load latencies overlap instead of following one another.
+        int ka = 0, kb = 0;
+        const int n8 = nrow2 * 8;
+        for (int p = tid; p < n8; p += 2 * NB_THREADS) {
+            const bool two = p + NB_THREADS < n8;
+            int sa[2], ga[2], gb[2];
+            bool va[2], vb[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int pu = p + u * NB_THREADS;
+                sa[u] = 16 * (pu >> 3) + (pu & 7);                            // slots sa, sa + 8: rows 2k and 2k+1, lane class jj
+                const int ea = slot_to_cand(sa[u]), eb = slot_to_cand(sa[u] + 8);
+                va[u] = (u == 0 || two) && ea < walk_total;                   // padding: never within the cutoff
+                vb[u] = (u == 0 || two) && eb < walk_total;
+                ga[u] = va[u] ? tile_to_global_fwd(R, ea, ka) : G.i0;         // (padding loads the first target: any valid row)
+                gb[u] = vb[u] ? tile_to_global_fwd(R, eb, kb) : G.i0;
             }
-            if (eb < walk_total) {
-                const int g = tile_to_global(R, eb);
-                b = P[g]; vb = true;
-                ub = make_float3((b.x - ccx) * sp.inv_h, (b.y - ccy) * sp.inv_h, (b.z - ccz) * sp.inv_h);
-                if (AKINCI) mb = __float_as_int(Q[g].z);
+            float4 a[2], b[2];
+            int ma[2] = {MAT_FLUID, MAT_FLUID}, mb[2] = {MAT_FLUID, MAT_FLUID};
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                a[u] = P[ga[u]];
+                b[u] = P[gb[u]];
+                if (AKINCI) { ma[u] = __float_as_int(Q[ga[u]].z); mb[u] = __float_as_int(Q[gb[u]].z); }
             }
-            TISPH_CHECK(sb < LT_SLOTS && p < LT_ROWS * 8);
-            // rounded coordinates and the norm of the ROUNDED vector (exact products in f32, one rounding to half)
-            const __half2 hx = __floats2half2_rn(ua.x, ub.x), hy = __floats2half2_rn(ua.y, ub.y), hz = __floats2half2_rn(ua.z, ub.z);
-            const float2 fx = __half22float2(hx), fy = __half22float2(hy), fz = __half22float2(hz);
-            const float na = va ? fmaf(fz.x, fz.x, fmaf(fy.x, fy.x, fx.x * fx.x)) : N_NEVER;
-            const float nb = vb ? fmaf(fz.y, fz.y, fmaf(fy.y, fy.y, fx.y * fx.y)) : N_NEVER;
-            T4[p] = make_uint4(h2_bits(hx), h2_bits(hy), h2_bits(hz), h2_bits(__floats2half2_rn(na, nb)));
-            GXY[sa] = make_float2(a.x, a.y); GZ[sa] = a.z;
-            GXY[sb] = make_float2(b.x, b.y); GZ[sb] = b.z;
-            if (AKINCI) { GM[sa] = ma; GM[sb] = mb; }
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int pu = p + u * NB_THREADS, sb = sa[u] + 8;
+                TISPH_CHECK(!(u == 0 || two) || (sb < LT_SLOTS && pu < LT_ROWS * 8));
+                const float4 far4 = make_float4(FAR, FAR, FAR, 0.f);
+                const float4 pa = va[u] ? a[u] : far4, pb = vb[u] ? b[u] : far4;
+                const float3 ua = va[u] ? make_float3((pa.x - ccx) * sp.inv_h, (pa.y - ccy) * sp.inv_h, (pa.z - ccz) * sp.inv_h)
+                                        : make_float3(0.f, 0.f, 0.f);
+                const float3 ub = vb[u] ? make_float3((pb.x - ccx) * sp.inv_h, (pb.y - ccy) * sp.inv_h, (pb.z - ccz) * sp.inv_h)
+                                        : make_float3(0.f, 0.f, 0.f);
+                // rounded coordinates and the norm of the ROUNDED vector (exact products in f32, one rounding to half)
+                const __half2 hx = __floats2half2_rn(ua.x, ub.x), hy = __floats2half2_rn(ua.y, ub.y), hz = __floats2half2_rn(ua.z, ub.z);
+                const float2 fx = __half22float2(hx), fy = __half22float2(hy), fz = __half22float2(hz);
+                const float na = va[u] ? fmaf(fz.x, fz.x, fmaf(fy.x, fy.x, fx.x * fx.x)) : N_NEVER;
+                const float nb = vb[u] ? fmaf(fz.y, fz.y, fmaf(fy.y, fy.y, fx.y * fx.y)) : N_NEVER;
+                if (u == 0 || two) {                                          // (only the stores of the second record are conditional)
+                    T4[pu] = make_uint4(h2_bits(hx), h2_bits(hy), h2_bits(hz), h2_bits(__floats2half2_rn(na, nb)));
+                    GXY[sa[u]] = make_float2(pa.x, pa.y); GZ[sa[u]] = pa.z;
+                    GXY[sb] = make_float2(pb.x, pb.y); GZ[sb] = pb.z;
+                    if (AKINCI) { GM[sa[u]] = va[u] ? ma[u] : MAT_FLUID; GM[sb] = vb[u] ? mb[u] : MAT_FLUID; }
+                }
+            }
         }
         __syncthreads();
         const int self_lo = R.gb[4], self_len = R.off[5] - R.off[4];
@@ -312,7 +331,18 @@ k_density_list(SimParams sp, const int* __restrict__ cell_end, const int2* __res
                 __half2 xi = __float2half2_rn(0.f), yi = xi, zi = xi;
                 uint32_t T = h2_bits(__float2half2_rn(-N_NEVER));      // idle lane: nothing survives
                 if (tf < G.nT) {
-                    const float4 pf = P[G.i0 + tf];
+                    // my target's position: it is in the tile (one of the cell's own particles), except in cell 0,
+                    // which is invisible as a neighbour cell (Q3), and in ghost cells that skip the walk
+                    const int itf = G.i0 + tf, st = itf - self_lo;
+                    float3 pf;
+                    if (walk_total > 0 && st >= 0 && st < self_len) {
+                        const int s = cand_to_slot(R.off[4] + st);
+                        const float2 xy = GXY[s];
+                        pf = make_float3(xy.x, xy.y, GZ[s]);
+                    } else {
+                        const float4 q4 = P[itf];
+                        pf = make_float3(q4.x, q4.y, q4.z);
+                    }
                     const __half hx = __float2half_rn((pf.x - ccx) * sp.inv_h), hy = __float2half_rn((pf.y - ccy) * sp.inv_h),
                                  hz = __float2half_rn((pf.z - ccz) * sp.inv_h);
                     const float fx = __half2float(hx), fy = __half2float(hy), fz = __half2float(hz);
@@ -636,8 +666,9 @@ k_force_list(SimParams sp, const int* __restrict__ cell_end, const int2* __restr
         const int row_p1 = npass > 1 ? item_row[(2 * it + 1) * 8 + (tid >> 5)] : row_p0;
         // ---- stage the tile: candidate e in slot cand_to_slot(e), six asynchronous copies each (psi comes ready-made
         //      from the density walk: D.z)
+        int kr = 0;                                                              // range of my last candidate (ascending)
         for (int e = tid; e < G.total; e += NB_THREADS) {
-            const int g = tile_to_global(R, e);
+            const int g = tile_to_global_fwd(R, e, kr);
             const uint32_t s8 = tP01 + 8u * (uint32_t)cand_to_slot(e);
             const float4 *pp = Pin + g, *vp = Vin + g, *dp = D + g;
             cp_async8(s8, pp);                                                   // P01 = {x, y}
@@ -657,17 +688,52 @@ k_force_list(SimParams sp, const int* __restrict__ cell_end, const int2* __restr
                 prefetch_l2(Lg + (size_t)(row_p1 + r) * 32 + (tid & 31));
             }
         }
+        // The head of a pass: the target's records, its list length and the first three list words.  None of it
+        // depends on the tile, so pass 0's head is asked for BEFORE the tile barrier and pass 1's behind pass 0's pair
+        // loop (before its reduction and epilogue): the latencies of these dependent loads (material and count row
+        // -> list words) are off the critical path.  The two passes are two copies of the code (static registers:
+        // a head that is still in flight is never moved).
+        struct PassHead {
+            float4 pi, vi, di, qi;
+            const uint32_t* gl;
+            int i, nw;
+            uint32_t w0, w1, w2;
+            bool active, walker;
+        };
+        auto load_head = [&](int pass) {
+            PassHead H;
+            const int t_local = pass * PASS_T + (tid >> 3);
+            H.i = G.i0 + t_local;
+            H.active = t_local < G.nT;
+            const int row = pass ? row_p1 : row_p0;
+            TISPH_CHECK(row >= 0);
+            const uint32_t* gl = Lg + (size_t)row * 32 + (tid & 31);
+            const int nw_row = (int)gl[0];                              // words of 4 entries (count row; written for every lane)
+            H.pi = H.active ? Pin[H.i] : make_float4(-FAR, -FAR, -FAR, 1.f);
+            H.vi = H.active ? Vin[H.i] : make_float4(0.f, 0.f, 0.f, 0.f);
+            H.di = H.active ? D[H.i] : make_float4(1.f, 0.f, 0.f, 0.f);
+            H.qi = H.active ? Qin[H.i] : make_float4(0.f, 0.f, 0.f, 0.f);
+            H.walker = H.active && __float_as_int(H.qi.z) == MAT_FLUID;
+            H.nw = H.walker ? nw_row : 0;
+            TISPH_CHECK(H.nw >= 0 && H.nw <= LCAP2 / 2);
+            gl += 32;
+            // list words are fetched three ahead of their use (a word is ~170 instructions of work); the rows behind
+            // the ones the staging prefetched are pulled into L2 now
+            H.w0 = H.nw > 0 ? gl[0] : 0u; H.w1 = H.nw > 1 ? gl[32] : 0u; H.w2 = H.nw > 2 ? gl[64] : 0u;
+            for (int r = 3; r < H.nw; ++r) prefetch_l2(gl + (size_t)r * 32);
+            H.gl = gl;
+            return H;
+        };
+        PassHead H0 = load_head(0), H1 = {};
         cp_async_wait_all();
         __syncthreads();
-        for (int pass = 0; pass < npass; ++pass) {
-            const int t_local = pass * PASS_T + (tid >> 3);
-            const int i = G.i0 + t_local;
-            const bool active = t_local < G.nT;
-            const float4 pi = active ? Pin[i] : make_float4(-FAR, -FAR, -FAR, 1.f);
-            const float4 vi = active ? Vin[i] : make_float4(0.f, 0.f, 0.f, 0.f);
-            const float4 di = active ? D[i] : make_float4(1.f, 0.f, 0.f, 0.f);
-            const float4 qi = active ? Qin[i] : make_float4(0.f, 0.f, 0.f, 0.f);
-            const bool walker = active && __float_as_int(qi.z) == MAT_FLUID;
+#pragma unroll
+        for (int pass = 0; pass < 2; ++pass) {
+            if (pass >= npass) break;
+            const PassHead& H = pass ? H1 : H0;
+            const int i = H.i;
+            const bool active = H.active, walker = H.walker;
+            const float4 pi = H.pi, vi = H.vi, di = H.di, qi = H.qi;
             const float coh_kw = 0.01f / pi.w * sp.k_w;                // wcsphv2.py:64 (x the kernel normalisation)
             const float rho_i = di.x, pr_i = di.y;
             const float nub_i = sp.visc_bound_c / (2.0f * rho_i);     // wcsphv2.py:76
@@ -680,14 +746,9 @@ k_force_list(SimParams sp, const int* __restrict__ cell_end, const int2* __restr
             C.nKpi = -C.K * pr_i;
             ForceAcc2 A;
             A.anx = A.any = A.anz = A.apx = A.apy = A.apz = make_float2(0.f, 0.f);
-            const int row = pass ? row_p1 : row_p0;
-            TISPH_CHECK(row >= 0);
-            const uint32_t* gl = Lg + (size_t)row * 32 + (tid & 31);
-            const int nw = walker ? (int)gl[0] : 0;                   // words of 4 entries (count row)
-            TISPH_CHECK(nw >= 0 && nw <= LCAP2 / 2);
-            gl += 32;
-            // list words are fetched three ahead of their use (a word is ~190 instructions of work)
-            uint32_t w0 = nw > 0 ? gl[0] : 0u, w1 = nw > 1 ? gl[32] : 0u, w2 = nw > 2 ? gl[64] : 0u;
+            const uint32_t* gl = H.gl;
+            const int nw = H.nw;
+            uint32_t w0 = H.w0, w1 = H.w1, w2 = H.w2;
             for (int k = 0; k < nw; ++k) {
                 const uint32_t cur = w0;
                 w0 = w1; w1 = w2;
@@ -706,6 +767,7 @@ k_force_list(SimParams sp, const int* __restrict__ cell_end, const int2* __restr
                                                      xy2, zp2, vxy2, make_float2(vz2, rp2.x), rp2.y, A);
                 }
             }
+            if (pass == 0 && npass > 1) H1 = load_head(1);            // in flight during the reduction and the epilogue
             float a6[6] = {A.anx.x + A.anx.y, A.any.x + A.any.y, A.anz.x + A.anz.y,
                            A.apx.x + A.apx.y, A.apy.x + A.apy.y, A.apz.x + A.apz.y};
 #pragma unroll
