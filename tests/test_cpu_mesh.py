@@ -27,3 +27,21 @@ def test_transform_matches_the_reference_order_of_operations():
     rel = v * 2 - c
     expect = c + np.stack([-rel[:, 1], rel[:, 0], rel[:, 2]], -1) + np.array([0.0, 1.0, 0.0])
     assert np.allclose(w, expect, atol=1e-12)
+
+
+def test_dragon_asset_is_closed_but_not_two_manifold():
+    """data/models/Dragon_50k.obj, the reference's only mesh (partice_systemv4.py:259-277): every edge carries two
+    faces except 16 that carry four, none is a boundary edge -- not "watertight" in trimesh's sense, but without
+    holes, which is all the outside-flood fill of the sampler needs."""
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    v, f = mesh.load_obj(os.path.join(root, "data", "models", "Dragon_50k.obj"))
+    assert v.shape == (25007, 3) and f.shape == (50000, 3) and len(np.unique(f)) == len(v)
+    e = np.sort(np.concatenate([f[:, [0, 1]], f[:, [1, 2]], f[:, [2, 0]]]), axis=1)
+    _, cnt = np.unique(e, axis=0, return_counts=True)
+    assert np.bincount(cnt).tolist() == [0, 0, 74968, 0, 16]
+    gold = np.load(os.path.join(root, "tests", "golden", "dragon_c4_voxels.npz"))
+    assert gold["edge_face_histogram"].tolist() == [0, 0, 74968, 0, 16]
+    surface = np.unpackbits(gold["surface"])[:int(np.prod(gold["dims"]))]
+    filled = np.unpackbits(gold["filled"])[:int(np.prod(gold["dims"]))]
+    assert (int(surface.sum()), int(filled.sum())) == (39759, 129815) and not np.any(surface & ~filled)
