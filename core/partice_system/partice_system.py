@@ -84,6 +84,28 @@ class ParticleSystem:
         self._kernel_stage = 0
         self.engine.stage(K.STAGE_UPDATE)
 
+    def allocate_particles_to_grid(self):
+        """partice_system.py:128-132 (dense cell lists).  The library builds the cell lists and the neighbour table
+        in ONE stage (TISPH_STAGE_UPDATE), so either of the two kernels of init() runs that stage for the current
+        state if it has not run yet, and the other one finds its result in place."""
+        if int(self.engine.get_param(K.P_PHASE)) == 0:
+            self.init()
+
+    def search_neighbors(self):
+        """partice_system.py:103-121 (neighbour table particle_neighbors / particle_neighbors_num)"""
+        if int(self.engine.get_param(K.P_PHASE)) == 0:
+            self.init()
+
+    def copy_to_numpy(self, np_arr, src_arr):
+        """partice_system.py:167-170: np_arr[i] = src_arr[i] for the particles in use"""
+        n = self.engine.particle_num
+        np_arr[:n] = src_arr.to_numpy()[:n]
+
+    def copy_to_numpy_nd(self, np_arr, src_arr):
+        """partice_system.py:172-176"""
+        n = self.engine.particle_num
+        np_arr[:n, :self.dim] = src_arr.to_numpy()[:n]
+
     def pos_to_index(self, pos):
         return (np.asarray(pos, np.float32) / np.float32(self.grid_size)).astype(np.int32)
 

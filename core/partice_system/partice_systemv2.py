@@ -12,6 +12,13 @@ class ParticleSystemV2(ParticleSystem):
         self.rigidBodiesConfig = simulation_config['rigidBodies']
         self.fluidBlocksConfig = simulation_config['fluidBlocks']
 
+    def load_rigid_body(self, rigid_body):
+        """partice_systemv2.py:67-85: OBJ -> boundary points at pitch = particle diameter.  add_fluid_and_rigid never
+        calls it (the call is commented out in the reference, :92-121); kept for scripts that do.  The reference's
+        2D class hands a 3D mesh to trimesh here; so does this one to the voxeliser (points are (n, 3))."""
+        from ti_sph_b200 import mesh
+        return mesh.sample_rigid_body(rigid_body, pitch=self.particle_diameter)
+
     def add_fluid_and_rigid(self):
         for fluid in self.fluidBlocksConfig:                                   # :124-136
             start, end = fluid['start'], fluid['end']

@@ -169,6 +169,13 @@ class ParticleSystemV4:
         self.prefix_sum_executor.run(self.grid_particles_num)
         self.resort()
 
+    def search_neighbors(self):
+        """partice_systemv4.py:310-330 is a leftover of the gen-1 class: it reads self.grid_particles,
+        self.particle_neighbors(_num) and self.support_radius, none of which ParticleSystemV4 defines, so the
+        reference raises as soon as Taichi compiles the kernel.  Same error here; gen-2 walks cells, it keeps no table."""
+        raise AttributeError("'ParticleSystemV4' object has no attribute 'grid_particles' "
+                             "(search_neighbors is dead code in the reference: partice_systemv4.py:310-330)")
+
     def copy_to_numpy(self, np_arr, src_arr):
         """partice_systemv4.py:298-301: np_arr[i] = src_arr[i] for the particles in use"""
         n = self.engine.particle_num

@@ -218,3 +218,36 @@ def test_gen1_kernel_by_kernel_driver_matches_the_reference_vectors(name):
     solver.step()
     assert ps._kernel_stage == 0
     ps.engine.close()
+
+
+def test_gen1_grid_and_neighbour_kernels_called_on_their_own():
+    """partice_system.py:211-215: init() is fill + allocate_particles_to_grid() + search_neighbors(); a script may call
+    the two kernels itself, and copy_to_numpy(_nd) (:167-176) instead of dump()"""
+    from core.partice_system.partice_system import ParticleSystem
+    from core.sph.wcsph import WCSPH
+    z = np.load(os.path.join(GOLD, "gen1_cube.npz"))
+    case = json.loads(str(z["case_json"]))
+    ps = ParticleSystem(tuple(case["res"]))
+    ps.add_cube(**case["cube"])
+    solver = WCSPH(ps)
+    ps.allocate_particles_to_grid()
+    ps.search_neighbors()
+    assert np.array_equal(ps.particle_neighbors.to_numpy(), z["s0.init.particle_neighbors"])
+    assert np.array_equal(ps.particle_neighbors_num.to_numpy(), z["s0.init.particle_neighbors_num"])
+    n = ps.particle_num[None]
+    x = np.zeros((n + 3, 2), np.float32)
+    mat = np.zeros(n + 3, np.int32)
+    ps.copy_to_numpy_nd(x, ps.x)
+    ps.copy_to_numpy(mat, ps.material)
+    assert np.array_equal(x[:n], z["init.x"]) and not x[n:].any()
+    assert np.array_equal(mat[:n], z["init.material"]) and not mat[n:].any()
+    solver.step()                                   # continues from the grid the two calls built
+    assert rel_err(ps.x.to_numpy(), z["s0.end.x"], floor=0.2) < RTOL
+    from ti_sph_b200 import _capi as K
+    assert int(ps.engine.get_param(K.P_PHASE)) == 0
+    ps.search_neighbors()                           # a new state: the kernel rebuilds grid and table
+    assert int(ps.engine.get_param(K.P_PHASE)) == 1
+    cnt = ps.particle_neighbors_num.to_numpy()
+    want = z["s1.init.particle_neighbors_num"]      # (the reference's own next state: knife-edge pairs of the lattice may flip)
+    assert cnt.shape == want.shape and np.abs(cnt.astype(np.int64) - want).max() <= 4 and (cnt == want).mean() > 0.9
+    ps.engine.close()
